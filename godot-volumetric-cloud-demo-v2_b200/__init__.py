@@ -1,0 +1,13 @@
+"""B200-native volumetric-cloud sky renderer — the hot path of
+clayjohn/godot-volumetric-cloud-demo-v2 (clouds.glsl + sky-lut.glsl + transmittance-lut.glsl and the
+cloud_sky.gd parameter surface) as hand-written sm_100a CUDA behind the C-ABI of include/cloudsky.h.
+
+Import name: ``cloudsky_b200`` (see cloudsky_b200.py at the repo root; the directory name
+``godot-volumetric-cloud-demo-v2_b200`` is not a valid Python identifier).
+"""
+from . import capi  # noqa: F401
+from .capi import (CloudParams, CloudSkyError, Context, Counters, FrameState, Library, SkySettings,  # noqa: F401
+                   MODE_FAST, MODE_STRICT, load_product)
+
+__all__ = ["capi", "CloudParams", "CloudSkyError", "Context", "Counters", "FrameState", "Library", "SkySettings",
+           "MODE_FAST", "MODE_STRICT", "load_product"]

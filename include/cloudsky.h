@@ -1,0 +1,245 @@
+/*
+ * cloudsky.h — C-ABI of the B200-native cloud-sky hot path.
+ *
+ * The reference (clayjohn/godot-volumetric-cloud-demo-v2) has no FFI / plugin API.
+ * Its operator boundary for this path is the Godot RenderingDevice compute dispatch:
+ * a push-constant block + descriptor sets + compute_list_dispatch
+ * (cloud_sky/cloud_sky.gd:234-248, sky_lut.gd:122-148, transmittance_lut.gd:51-78).
+ * Every entry point below names the reference interface it replaces (file:line,
+ * paths relative to the reference root).
+ *
+ * Plain C: opaque context pointer, plain pointers and sizes, int return codes
+ * (0 = CS_OK).  Never aborts; on error the code is returned and
+ * cs_last_error(ctx) holds a message (the reference only has boolean flags + prints:
+ * cloud_sky.gd:96,130-131,362-364; sky_lut.gd:45-47).
+ *
+ * Two shared libraries implement this same header:
+ *   libcloudsky_b200.so   — the product: hand-written sm_100a CUDA (this repo's csrc/)
+ *   libcloudsky_oracle.so — TEST INFRASTRUCTURE ONLY: scalar fp32 CPU restatement (oracle/)
+ *
+ * Threading: one context = one CUDA device + one stream.  Calls on one context are
+ * not thread-safe; different contexts are independent (the reference marshals all GPU
+ * work to a single render thread: cloud_sky.gd:118,154).
+ */
+#ifndef CLOUDSKY_H
+#define CLOUDSKY_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CS_OK 0
+#define CS_ERR_INVALID 1     /* bad argument / bad state                              */
+#define CS_ERR_CUDA 2        /* CUDA runtime failure (message in cs_last_error)       */
+#define CS_ERR_IO 3          /* asset file could not be read / decoded                */
+#define CS_ERR_UNSUPPORTED 4 /* e.g. CUDA call on the oracle backend                  */
+#define CS_ERR_NOT_READY 5   /* textures / LUTs missing ("can_run == false")          */
+
+/* Fixed sizes of the two atmosphere LUTs. */
+#define CS_TRANSMITTANCE_W 256 /* transmittance_lut.gd:6 */
+#define CS_TRANSMITTANCE_H 64
+#define CS_SKY_LUT_W 200 /* sky_lut.gd:4 */
+#define CS_SKY_LUT_H 100
+
+/* Reference march constants (clouds.glsl:228 and :186). */
+#define CS_REF_PRIMARY_STEPS 128
+#define CS_REF_CONE_SAMPLES 6
+
+typedef struct cs_context cs_context;
+
+/*
+ * The 112-byte std430 push-constant block of clouds.glsl (clouds.glsl:18-40), in the
+ * exact order cloud_sky.gd:_fill_push_constant packs it (cloud_sky.gd:251-289), so a
+ * Godot-side caller can memcpy its PackedFloat32Array into this struct.
+ */
+typedef struct cs_cloud_params {
+    float texture_size[2];    /* @0   W, H of the hemisphere texture (pixels)            */
+    float update_position[2]; /* @8   pixel origin of the tile being dispatched          */
+    float cloud_pos[2];       /* @16  base wind offset                                   */
+    float detailed_pos[2];    /* @24  detail wind offset                                 */
+    float weather_pos[2];     /* @32  weather-map offset                                 */
+    float pad1[2];            /* @40                                                     */
+    float ground_color[4];    /* @48                                                     */
+    float light_direction[3]; /* @64  unit vector TOWARD the sun (cloud_sky.gd:76-79)    */
+    float light_energy;       /* @76                                                     */
+    float light_color[3];     /* @80  linear RGB                                         */
+    float time;               /* @92  absolute seconds (cloud_sky.gd:282)                */
+    float pad2;               /* @96                                                     */
+    float density;            /* @100                                                    */
+    float cloud_coverage;     /* @104                                                    */
+    float time_offset;        /* @108 pushed but unused by the shader                    */
+} cs_cloud_params;
+
+/* User-level parameter surface: the @export properties of cloud_sky.gd:4-50. */
+typedef struct cs_sky_settings {
+    float wind_direction;  /* radians (cloud_sky.gd:9-10)                              */
+    float wind_speed;      /* m/s     (cloud_sky.gd:13-14)                             */
+    float density;         /* cloud_sky.gd:19-20                                       */
+    float cloud_coverage;  /* cloud_sky.gd:21-22                                       */
+    float time_offset;     /* cloud_sky.gd:23-24                                       */
+    float sun_disk_scale;  /* cloud_sky.gd:27-31 (presentation only)                   */
+    float ground_color[4]; /* cloud_sky.gd:32-33                                       */
+    int32_t frames_to_update; /* 4 / 16 / 64 / 256 (cloud_sky.gd:36-42); 1 = one dispatch */
+    int32_t texture_size;     /* cloud_sky.gd:44-50                                    */
+} cs_sky_settings;
+
+/* FrameData's derived state (cloud_sky.gd:56-79): wind accumulators + light snapshot. */
+typedef struct cs_frame_state {
+    float time;            /* _time          cloud_sky.gd:66 */
+    float cloud_pos[2];    /* _cloud_pos     cloud_sky.gd:67 */
+    float detailed_pos[2]; /* _detailed_pos  cloud_sky.gd:68 */
+    float weather_pos[2];  /* _weather_pos   cloud_sky.gd:69 */
+    float light_direction[3]; /* LIGHT_DIRECTION cloud_sky.gd:72 */
+    float light_energy;       /* LIGHT_ENERGY    cloud_sky.gd:73 */
+    float light_color[3];     /* LIGHT_COLOR (linear) cloud_sky.gd:74 */
+} cs_frame_state;
+
+/* Work counters of the last instrumented clouds dispatch. */
+typedef struct cs_counters {
+    uint64_t marched_pixels;    /* pixels with dir.y > 0                                   */
+    uint64_t primary_steps;     /* executed primary-loop iterations                        */
+    uint64_t lit_steps;         /* primary steps with t > 0 (light march executed)         */
+    uint64_t density_evals;     /* calls of density() (primary + cone + distant)           */
+    uint64_t large_fetches;     /* trilinear fetches of the large volume actually issued   */
+    uint64_t small_fetches;     /* trilinear fetches of the small volume actually issued   */
+} cs_counters;
+
+/* march mode flags for cs_set_march_config */
+#define CS_MODE_FAST 0   /* product kernel: FMA contraction, fast intrinsics, exact-zero skips */
+#define CS_MODE_STRICT 1 /* same operation order as the oracle, --fmad=false, IEEE div/sqrt  */
+
+/* ---- lifetime -------------------------------------------------------------------------- */
+
+/* Replaces _initialize_compute_code (cloud_sky.gd:355-408): device/pipeline setup.
+ * device = CUDA ordinal (ignored by the oracle backend). */
+int cs_create(int device, cs_context** out_ctx);
+/* Replaces cleanup() / NOTIFICATION_PREDELETE (cloud_sky.gd:193-212, sky_lut.gd:29-37,
+ * transmittance_lut.gd:20-25). */
+void cs_destroy(cs_context* ctx);
+/* Replaces the print()-based error reporting (sky_lut.gd:45-47,105-107). */
+const char* cs_last_error(const cs_context* ctx);
+/* "cuda-sm100a" or "oracle-cpu". */
+const char* cs_backend_name(void);
+/* Use an existing cudaStream_t (e.g. torch's current stream) for all work of this context.
+ * NULL = the context's own stream.  (Godot: the render-thread queue, cloud_sky.gd:154.) */
+int cs_set_stream(cs_context* ctx, void* cuda_stream);
+/* Wait for all work queued on the context's stream. */
+int cs_sync(cs_context* ctx);
+/* Worker threads for the oracle backend (no-op for CUDA). */
+int cs_set_threads(cs_context* ctx, int n_threads);
+
+/* ---- input textures (set 1 bindings 0/1/2; cloud_sky.gd:298-341, clouds.glsl:10-12) ------ */
+
+/* large: n^3 texels, `large_ch` (4) bytes per texel, x fastest then y then z (texel (x,y,z) of
+ *        the sliced strip: perlworlnoise.tga.import:24-27);
+ * small: n^3 texels, 3 or 4 bytes per texel (worlnoise.bmp.import:24-27);
+ * weather: w*h texels, 3 or 4 bytes per texel, row 0 = v 0 (weather.bmp.import:25, no mips).
+ * The library copies the data and builds the box-filter mip chains of the two volumes. */
+int cs_upload_textures(cs_context* ctx,
+                       const uint8_t* large, int large_n, int large_ch,
+                       const uint8_t* small, int small_n, int small_ch,
+                       const uint8_t* weather, int weather_w, int weather_h, int weather_ch);
+/* Replaces preload("perlworlnoise.tga") / preload("worlnoise.bmp") / preload("weather.bmp")
+ * (cloud_sky.gd:311,321,331): decodes RLE TGA / BI_RGB BMP strips and slices them
+ * horizontally (slices/horizontal, *.import:26). */
+int cs_load_texture_files(cs_context* ctx, const char* large_path, int large_slices,
+                          const char* small_path, int small_slices, const char* weather_path);
+/* Stand-alone decoder used by the call above: returns malloc'ed top-row-first RGB(A) bytes
+ * (free with cs_free). */
+int cs_decode_image_file(const char* path, uint8_t** out_pixels, int* out_w, int* out_h,
+                         int* out_channels);
+void cs_free(void* p);
+/* Read back one mip level of the large (which=0) or small (which=1) volume as RGBA8
+ * (level 0 = the upload).  out must hold (n>>level)^3*4 bytes. */
+int cs_read_volume_level(cs_context* ctx, int which, int level, uint8_t* out, size_t out_bytes);
+
+/* ---- atmosphere LUTs -------------------------------------------------------------------- */
+
+/* Replaces transmittance_lut.gd:_initialize_compute_code's one dispatch (32x8 groups,
+ * transmittance_lut.gd:66-78) of transmittance-lut.glsl:157-196.  256x64 RGBA16F. */
+int cs_build_transmittance_lut(cs_context* ctx);
+/* Replaces SkyLUT.update_lut(sun_direction) -> render_lut (sky_lut.gd:43-52,122-148):
+ * one dispatch of sky-lut.glsl:278-315.  200x100 RGBA16F.  Needs the transmittance LUT. */
+int cs_build_sky_lut(cs_context* ctx, const float sun_direction[3]);
+/* Readback / injection of the two LUTs as tightly packed half4 texels (row 0 = v 0). */
+int cs_read_transmittance_lut(cs_context* ctx, uint16_t* out_half4, size_t out_bytes);
+int cs_read_sky_lut(cs_context* ctx, uint16_t* out_half4, size_t out_bytes);
+int cs_write_transmittance_lut(cs_context* ctx, const uint16_t* half4, size_t bytes);
+int cs_write_sky_lut(cs_context* ctx, const uint16_t* half4, size_t bytes);
+
+/* ---- the cloud march (set 0 binding 0 output; cloud_sky.gd:234-248) ----------------------- */
+
+/* (Re)allocate the RGBA16F output image (cloud_sky.gd:368-376,399).  W != H is allowed
+ * (clouds.glsl:19 texture_size is a vec2). */
+int cs_resize(cs_context* ctx, int width, int height);
+/* Step-count parametrisation (extension; the reference is fixed at 128 primary steps,
+ * clouds.glsl:228, and 6 cone + 1 distant light samples, clouds.glsl:186-199).
+ * mode = CS_MODE_FAST or CS_MODE_STRICT.  SURVEY §8(d) rule: cone sample j uses
+ * RANDOM_VECTORS[j % 6] * j and mip j, LODs clamp to the last mip. */
+int cs_set_march_config(cs_context* ctx, int primary_steps, int cone_samples, int mode);
+/* Enable/disable the device work counters (slower instrumented kernel when enabled). */
+int cs_set_counters_enabled(cs_context* ctx, int enabled);
+int cs_get_counters(cs_context* ctx, cs_counters* out);
+
+/* Replaces compute_list_dispatch(num_workgroups, num_workgroups, 1) of clouds.glsl with
+ * 8x8 groups (cloud_sky.gd:247, clouds.glsl:5,258-266): renders pixels
+ * [update_position, update_position + 8*groups) clipped to the image (the reference does
+ * not bounds-check; this does).  Asynchronous on the context's stream. */
+int cs_dispatch_clouds(cs_context* ctx, const cs_cloud_params* params, int groups_x, int groups_y);
+/* Whole image in one dispatch (north_star's "single dispatch"); params->update_position is
+ * ignored (treated as 0,0). */
+int cs_render_frame(cs_context* ctx, const cs_cloud_params* params);
+/* Same, writing into caller-owned DEVICE memory (tightly packed half4[W*H]); used to render
+ * straight into a shard of a gathered buffer.  rows [row_begin,row_end) only. */
+int cs_render_rows_to(cs_context* ctx, const cs_cloud_params* params, int row_begin, int row_end,
+                      void* device_out_half4);
+/* Device pointer of the context-owned output image (Texture2DRD handle, cloud_sky.gd:235). */
+void* cs_image_device_ptr(cs_context* ctx);
+/* Copy the context-owned image to host: tightly packed half4[W*H], row 0 = uv.y 0. */
+int cs_read_image(cs_context* ctx, uint16_t* out_half4, size_t out_bytes);
+/* End-to-end convenience with HOST buffers: sky LUT for params->light_direction, full-frame
+ * render, device->host copy into (pinned or pageable) out_half4, synchronised on return.
+ * This is the _update_per_frame_data + _render_process pair (cloud_sky.gd:165-187,234-248). */
+int cs_render_frame_host(cs_context* ctx, const cs_cloud_params* params, uint16_t* out_half4,
+                         size_t out_bytes);
+/* Sun-angle batch (BASELINE config 4): for each of n suns build its sky LUT and render one full
+ * frame into device_out_half4 + i*W*H*4 halfs.  Other params are shared. */
+int cs_render_sun_batch_to(cs_context* ctx, const cs_cloud_params* params, const float* sun_dirs_xyz,
+                           int n_suns, void* device_out_half4);
+/* Device-side timing of `iters` back-to-back full-frame dispatches with CUDA events on the
+ * context's stream (after `warmup` untimed ones).  Returns average milliseconds per dispatch. */
+int cs_time_render_frame(cs_context* ctx, const cs_cloud_params* params, int warmup, int iters,
+                         float* out_ms_avg);
+
+/* ---- host-side parameter logic (pure CPU, no context) ------------------------------------ */
+
+/* Script defaults of cloud_sky.gd:4-50 (coverage 0.25, white ground, 768, 64 frames). */
+void cs_settings_default(cs_sky_settings* s);
+/* Demo resource values of clouds_sky.tres:11-18 (coverage 0.2, brown ground, sun_disk 2). */
+void cs_settings_demo(cs_sky_settings* s);
+/* FrameData initial values (cloud_sky.gd:66-74): zero offsets, light (0,-1,0), energy 1, white. */
+void cs_frame_state_init(cs_frame_state* st);
+/* FrameData.update_light_data (cloud_sky.gd:76-79): direction = normalize(basis * (0,0,1)) with
+ * basis given as 3 column vectors (Godot Basis x,y,z axes); colour sRGB -> linear. */
+void cs_frame_state_set_light(cs_frame_state* st, const float basis_columns[9], float energy,
+                              const float color_srgb[3]);
+/* _update_per_frame_data (cloud_sky.gd:165-187) with the clock passed in: integrates the three
+ * wind offsets from st->time to abs_time_seconds and stores the new time. */
+void cs_frame_advance(cs_frame_state* st, const cs_sky_settings* s, float abs_time_seconds);
+/* _fill_push_constant (cloud_sky.gd:251-289). */
+void cs_fill_cloud_params(cs_cloud_params* out, const cs_sky_settings* s, const cs_frame_state* st,
+                          int width, int height, int update_x, int update_y);
+/* update_performance (cloud_sky.gd:109-118): region = texture_size / isqrt(frames_to_update),
+ * texture_size coerced to a multiple, groups = ceil(region / 8). */
+void cs_update_performance(int* texture_size_inout, int frames_to_update, int* out_region,
+                           int* out_groups);
+/* The raster-order tile walk of update_sky (cloud_sky.gd:156-161). */
+void cs_next_update_position(int* x_inout, int* y_inout, int region, int texture_size);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLOUDSKY_H */
