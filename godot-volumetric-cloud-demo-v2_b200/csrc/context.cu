@@ -1,0 +1,477 @@
+// libcloudsky_b200.so — context management and the C-ABI of include/cloudsky.h on top of the
+// sm_100a kernels (lut_kernels.cu, clouds_strict.cu, clouds_fast.cu).
+//
+// HBM layout per context (everything stays resident; the whole working set is ~13 MiB and lives
+// in L2 after the first frame):
+//   large volume : RGBA8 mip chain 128^3 .. 1^3 (9.14 MiB) + packed 2-channel chain for the fast kernel
+//   small volume : RGBA8 mip chain 32^3 .. 1^3 (146 KiB)   + packed 1-channel chain
+//   weather map  : RGBA8 512^2 (1 MiB)                     + packed (R,B) map
+//   transmittance LUT 256x64 half4, sky LUT 200x100 half4, FrameConsts (64 B)
+//   output image : W*H half4, tightly packed, row 0 = uv.y 0
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "cs_internal.h"
+
+using namespace cs;
+
+struct cs_context {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string err;
+
+    // textures
+    bool have_tex = false;
+    int large_n = 0, large_levels = 0, small_n = 0, small_levels = 0, weather_w = 0, weather_h = 0;
+    uint32_t* d_large[kMaxLargeLevels] = {};
+    uint32_t* d_small[kMaxSmallLevels] = {};
+    uint32_t* d_weather = nullptr;
+    uint32_t* d_large_pk[kMaxLargeLevels] = {};
+    uint16_t* d_small_pk[kMaxSmallLevels] = {};
+    uint32_t* d_weather_pk = nullptr;
+    std::vector<std::vector<uint8_t>> h_large, h_small;  // host copies of the mip chains (readback / repack)
+
+    // LUTs
+    uint16_t* d_tlut = nullptr;
+    uint16_t* d_sky = nullptr;
+    bool have_tlut = false, have_sky = false;
+    float* d_frame_consts = nullptr;
+
+    // output
+    int W = 0, H = 0;
+    uint16_t* d_image = nullptr;
+
+    // march config
+    int primary_steps = CS_REF_PRIMARY_STEPS, cone_samples = CS_REF_CONE_SAMPLES, mode = CS_MODE_FAST;
+    bool counters_on = false;
+    unsigned long long* d_counters = nullptr;
+};
+
+namespace {
+
+int fail(cs_context* c, int code, const std::string& msg) {
+    if (c) c->err = msg;
+    return code;
+}
+int cuda_fail(cs_context* c, cudaError_t e, const char* what) {
+    return fail(c, CS_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU(call)                                                     \
+    do {                                                             \
+        cudaError_t e__ = (call);                                    \
+        if (e__ != cudaSuccess) return cuda_fail(c, e__, #call);     \
+    } while (0)
+
+int bind(cs_context* c) {
+    CU(cudaSetDevice(c->device));
+    return CS_OK;
+}
+
+void free_textures(cs_context* c) {
+    for (auto& p : c->d_large) { if (p) cudaFree(p); p = nullptr; }
+    for (auto& p : c->d_small) { if (p) cudaFree(p); p = nullptr; }
+    for (auto& p : c->d_large_pk) { if (p) cudaFree(p); p = nullptr; }
+    for (auto& p : c->d_small_pk) { if (p) cudaFree(p); p = nullptr; }
+    if (c->d_weather) cudaFree(c->d_weather);
+    if (c->d_weather_pk) cudaFree(c->d_weather_pk);
+    c->d_weather = nullptr; c->d_weather_pk = nullptr;
+    c->have_tex = false;
+}
+
+bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+// Packed layouts for the fast kernel: only the channel combinations clouds.glsl reads, as exact
+// integers.  large: lo16 = R (0..255), hi16 = 5G + 2B + A (0..2040, = 8 * 255 * fbm, clouds.glsl:118);
+// small: 5R + 2G + B (= 8 * 255 * hfbm, clouds.glsl:133); weather: lo16 = R, hi16 = B (clouds.glsl:121,123).
+void pack_large(const std::vector<uint8_t>& rgba, std::vector<uint32_t>& out) {
+    size_t n = rgba.size() / 4;
+    out.resize(n);
+    for (size_t i = 0; i < n; i++) {
+        uint32_t r = rgba[i * 4], g = rgba[i * 4 + 1], b = rgba[i * 4 + 2], a = rgba[i * 4 + 3];
+        out[i] = r | ((5u * g + 2u * b + a) << 16);
+    }
+}
+void pack_small(const std::vector<uint8_t>& rgba, std::vector<uint16_t>& out) {
+    size_t n = rgba.size() / 4;
+    out.resize(n);
+    for (size_t i = 0; i < n; i++) out[i] = (uint16_t)(5u * rgba[i * 4] + 2u * rgba[i * 4 + 1] + rgba[i * 4 + 2]);
+}
+void pack_weather(const std::vector<uint8_t>& rgba, std::vector<uint32_t>& out) {
+    size_t n = rgba.size() / 4;
+    out.resize(n);
+    for (size_t i = 0; i < n; i++) out[i] = (uint32_t)rgba[i * 4] | ((uint32_t)rgba[i * 4 + 2] << 16);
+}
+
+int upload_levels(cs_context* c, const std::vector<uint8_t>& large0, int ln, const std::vector<uint8_t>& small0, int sn,
+                  const std::vector<uint8_t>& weather, int ww, int wh) {
+    if (!is_pow2(ln) || !is_pow2(sn) || !is_pow2(ww) || !is_pow2(wh))
+        return fail(c, CS_ERR_INVALID, "texture dimensions must be powers of two (REPEAT addressing uses masks)");
+    if (ln > 128 || sn > 32) return fail(c, CS_ERR_INVALID, "volume too large (large <= 128^3, small <= 32^3)");
+    int r = bind(c);
+    if (r) return r;
+    CU(cudaStreamSynchronize(c->stream));
+    free_textures(c);
+    c->h_large.assign(1, large0);
+    c->h_small.assign(1, small0);
+    build_volume_mips(c->h_large, ln);
+    build_volume_mips(c->h_small, sn);
+    c->large_n = ln; c->large_levels = (int)c->h_large.size();
+    c->small_n = sn; c->small_levels = (int)c->h_small.size();
+    c->weather_w = ww; c->weather_h = wh;
+    std::vector<uint32_t> pk;
+    for (int l = 0; l < c->large_levels; l++) {
+        CU(cudaMalloc(&c->d_large[l], c->h_large[l].size()));
+        CU(cudaMemcpy(c->d_large[l], c->h_large[l].data(), c->h_large[l].size(), cudaMemcpyHostToDevice));
+        pack_large(c->h_large[l], pk);
+        CU(cudaMalloc(&c->d_large_pk[l], pk.size() * 4));
+        CU(cudaMemcpy(c->d_large_pk[l], pk.data(), pk.size() * 4, cudaMemcpyHostToDevice));
+    }
+    std::vector<uint16_t> pk16;
+    for (int l = 0; l < c->small_levels; l++) {
+        CU(cudaMalloc(&c->d_small[l], c->h_small[l].size()));
+        CU(cudaMemcpy(c->d_small[l], c->h_small[l].data(), c->h_small[l].size(), cudaMemcpyHostToDevice));
+        pack_small(c->h_small[l], pk16);
+        CU(cudaMalloc(&c->d_small_pk[l], pk16.size() * 2 + 16));
+        CU(cudaMemcpy(c->d_small_pk[l], pk16.data(), pk16.size() * 2, cudaMemcpyHostToDevice));
+    }
+    CU(cudaMalloc(&c->d_weather, weather.size()));
+    CU(cudaMemcpy(c->d_weather, weather.data(), weather.size(), cudaMemcpyHostToDevice));
+    pack_weather(weather, pk);
+    CU(cudaMalloc(&c->d_weather_pk, pk.size() * 4));
+    CU(cudaMemcpy(c->d_weather_pk, pk.data(), pk.size() * 4, cudaMemcpyHostToDevice));
+    c->have_tex = true;
+    return CS_OK;
+}
+
+int make_launch(cs_context* c, const cs_cloud_params* P, int x0, int y0, int x1, int y1, uint16_t* out, CloudLaunch& L) {
+    if (!c->have_tex) return fail(c, CS_ERR_NOT_READY, "input textures not uploaded (can_run == false)");
+    if (!c->have_sky) return fail(c, CS_ERR_NOT_READY, "sky LUT not built (Attempting to render with an uninitialized sky lut)");
+    if (c->W < 1 || !out) return fail(c, CS_ERR_NOT_READY, "cs_resize not called");
+    if ((int)P->texture_size[0] != c->W || (int)P->texture_size[1] != c->H)
+        return fail(c, CS_ERR_INVALID, "params.texture_size does not match the image size set with cs_resize");
+    std::memset(&L, 0, sizeof(L));
+    L.P = *P;
+    L.width = c->W; L.height = c->H;
+    L.x0 = x0 < 0 ? 0 : x0; L.y0 = y0 < 0 ? 0 : y0;
+    L.x1 = x1 > c->W ? c->W : x1; L.y1 = y1 > c->H ? c->H : y1;
+    L.out_pitch_px = c->W;
+    L.primary_steps = c->primary_steps; L.cone_samples = c->cone_samples;
+    L.large_n = c->large_n; L.large_levels = c->large_levels;
+    L.small_n = c->small_n; L.small_levels = c->small_levels;
+    L.weather_w = c->weather_w; L.weather_h = c->weather_h;
+    for (int l = 0; l < kMaxLargeLevels; l++) { L.large[l] = c->d_large[l]; L.large_pk[l] = c->d_large_pk[l]; }
+    for (int l = 0; l < kMaxSmallLevels; l++) { L.small[l] = c->d_small[l]; L.small_pk[l] = c->d_small_pk[l]; }
+    L.weather = c->d_weather; L.weather_pk = c->d_weather_pk;
+    L.sky_lut = c->d_sky;
+    L.frame_consts = c->d_frame_consts;
+    L.out = out;
+    L.counters = c->counters_on ? c->d_counters : nullptr;
+    return CS_OK;
+}
+
+// prologue + march for one rectangle, asynchronous on c->stream
+int dispatch(cs_context* c, const cs_cloud_params* P, int x0, int y0, int x1, int y1, uint16_t* out) {
+    if (!c || !P) return CS_ERR_INVALID;
+    int r = bind(c);
+    if (r) return r;
+    CloudLaunch L;
+    r = make_launch(c, P, x0, y0, x1, y1, out, L);
+    if (r) return r;
+    if (L.x1 <= L.x0 || L.y1 <= L.y0) return CS_OK;
+    if (L.counters) CU(cudaMemsetAsync(c->d_counters, 0, 6 * sizeof(unsigned long long), c->stream));
+    launch_clouds_prologue(L, c->mode == CS_MODE_STRICT, c->stream);
+    if (c->mode == CS_MODE_STRICT) launch_clouds_strict(L, c->stream);
+    else launch_clouds_fast(L, c->stream);
+    CU(cudaGetLastError());
+    return CS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cs_create(int device, cs_context** out) {
+    if (!out) return CS_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || device < 0 || device >= count) {
+        fprintf(stderr, "cloudsky_b200: cs_create(device=%d) failed: %s (devices: %d). There is no CPU fallback.\n", device,
+                e != cudaSuccess ? cudaGetErrorString(e) : "no such device", count);
+        return CS_ERR_CUDA;
+    }
+    cs_context* c = new cs_context();
+    c->device = device;
+    bool ok = cudaSetDevice(device) == cudaSuccess && cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaMalloc(&c->d_tlut, (size_t)CS_TRANSMITTANCE_W * CS_TRANSMITTANCE_H * 8) == cudaSuccess &&
+              cudaMalloc(&c->d_sky, (size_t)CS_SKY_LUT_W * CS_SKY_LUT_H * 8) == cudaSuccess &&
+              cudaMalloc(&c->d_frame_consts, sizeof(FrameConsts)) == cudaSuccess &&
+              cudaMalloc(&c->d_counters, 6 * sizeof(unsigned long long)) == cudaSuccess;
+    if (!ok) {
+        fprintf(stderr, "cloudsky_b200: cs_create: %s\n", cudaGetErrorString(cudaGetLastError()));
+        cs_destroy(c);
+        return CS_ERR_CUDA;
+    }
+    c->stream = c->own_stream;
+    *out = c;
+    return CS_OK;
+}
+
+void cs_destroy(cs_context* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    free_textures(c);
+    if (c->d_tlut) cudaFree(c->d_tlut);
+    if (c->d_sky) cudaFree(c->d_sky);
+    if (c->d_frame_consts) cudaFree(c->d_frame_consts);
+    if (c->d_counters) cudaFree(c->d_counters);
+    if (c->d_image) cudaFree(c->d_image);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+const char* cs_last_error(const cs_context* c) { return c ? c->err.c_str() : "null context"; }
+const char* cs_backend_name(void) { return "cuda-sm100a"; }
+
+int cs_set_stream(cs_context* c, void* s) {
+    if (!c) return CS_ERR_INVALID;
+    int r = bind(c);
+    if (r) return r;
+    CU(cudaStreamSynchronize(c->stream));
+    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    return CS_OK;
+}
+int cs_sync(cs_context* c) {
+    if (!c) return CS_ERR_INVALID;
+    int r = bind(c);
+    if (r) return r;
+    CU(cudaStreamSynchronize(c->stream));
+    return CS_OK;
+}
+int cs_set_threads(cs_context* c, int) { return c ? CS_OK : CS_ERR_INVALID; }
+
+int cs_upload_textures(cs_context* c, const uint8_t* large, int ln, int lch, const uint8_t* small, int sn, int sch,
+                       const uint8_t* weather, int ww, int wh, int wch) {
+    if (!c) return CS_ERR_INVALID;
+    if (!large || !small || !weather || ln < 1 || sn < 1 || ww < 1 || wh < 1 || lch < 3 || lch > 4 || sch < 3 || sch > 4 || wch < 3 || wch > 4)
+        return fail(c, CS_ERR_INVALID, "cs_upload_textures: null pointer or bad dimensions / channel count");
+    std::vector<uint8_t> l0, s0, w0;
+    expand_rgba(large, (size_t)ln * ln * ln, lch, l0);
+    expand_rgba(small, (size_t)sn * sn * sn, sch, s0);
+    expand_rgba(weather, (size_t)ww * wh, wch, w0);
+    return upload_levels(c, l0, ln, s0, sn, w0, ww, wh);
+}
+
+int cs_load_texture_files(cs_context* c, const char* large_path, int large_slices, const char* small_path, int small_slices,
+                          const char* weather_path) {
+    if (!c) return CS_ERR_INVALID;
+    HostImage li, si, wi;
+    std::string e = decode_image_file(large_path, li);
+    if (!e.empty()) return fail(c, CS_ERR_IO, e);
+    e = decode_image_file(small_path, si);
+    if (!e.empty()) return fail(c, CS_ERR_IO, e);
+    e = decode_image_file(weather_path, wi);
+    if (!e.empty()) return fail(c, CS_ERR_IO, e);
+    std::vector<uint8_t> l0, s0, w0;
+    int ln = 0, sn = 0;
+    e = strip_to_volume_rgba(li, large_slices, l0, ln);
+    if (!e.empty()) return fail(c, CS_ERR_IO, std::string(large_path) + ": " + e);
+    e = strip_to_volume_rgba(si, small_slices, s0, sn);
+    if (!e.empty()) return fail(c, CS_ERR_IO, std::string(small_path) + ": " + e);
+    expand_rgba(wi.px.data(), (size_t)wi.w * wi.h, wi.ch, w0);
+    return upload_levels(c, l0, ln, s0, sn, w0, wi.w, wi.h);
+}
+
+int cs_decode_image_file(const char* path, uint8_t** out_pixels, int* w, int* h, int* ch) {
+    if (!path || !out_pixels || !w || !h || !ch) return CS_ERR_INVALID;
+    HostImage im;
+    std::string e = decode_image_file(path, im);
+    if (!e.empty()) return CS_ERR_IO;
+    uint8_t* p = (uint8_t*)malloc(im.px.size());
+    if (!p) return CS_ERR_IO;
+    memcpy(p, im.px.data(), im.px.size());
+    *out_pixels = p; *w = im.w; *h = im.h; *ch = im.ch;
+    return CS_OK;
+}
+void cs_free(void* p) { free(p); }
+
+int cs_read_volume_level(cs_context* c, int which, int level, uint8_t* out, size_t bytes) {
+    if (!c || !out) return CS_ERR_INVALID;
+    if (!c->have_tex) return fail(c, CS_ERR_NOT_READY, "no textures");
+    int levels = which == 0 ? c->large_levels : c->small_levels;
+    if (which < 0 || which > 1 || level < 0 || level >= levels) return fail(c, CS_ERR_INVALID, "bad volume / level");
+    const uint32_t* d = which == 0 ? c->d_large[level] : c->d_small[level];
+    int n = (which == 0 ? c->large_n : c->small_n) >> level;
+    if (bytes != (size_t)n * n * n * 4) return fail(c, CS_ERR_INVALID, "bad output size");
+    int r = bind(c);
+    if (r) return r;
+    CU(cudaMemcpy(out, d, bytes, cudaMemcpyDeviceToHost));  // read back what the kernels actually sample
+    return CS_OK;
+}
+
+int cs_build_transmittance_lut(cs_context* c) {
+    if (!c) return CS_ERR_INVALID;
+    int r = bind(c);
+    if (r) return r;
+    launch_transmittance_lut(c->d_tlut, c->stream);
+    CU(cudaGetLastError());
+    c->have_tlut = true;
+    return CS_OK;
+}
+int cs_build_sky_lut(cs_context* c, const float sun[3]) {
+    if (!c || !sun) return CS_ERR_INVALID;
+    if (!c->have_tlut) return fail(c, CS_ERR_NOT_READY, "Attempting to update uninitialized sky lut (build the transmittance LUT first)");
+    int r = bind(c);
+    if (r) return r;
+    launch_sky_lut(c->d_tlut, sun, c->d_sky, c->stream);
+    CU(cudaGetLastError());
+    c->have_sky = true;
+    return CS_OK;
+}
+
+static int read_dev(cs_context* c, const void* d, void* out, size_t bytes, size_t expect, bool ready, const char* what) {
+    if (!c || !out) return CS_ERR_INVALID;
+    if (!ready) return fail(c, CS_ERR_NOT_READY, std::string(what) + " not built");
+    if (bytes != expect) return fail(c, CS_ERR_INVALID, std::string(what) + ": bad buffer size");
+    int r = bind(c);
+    if (r) return r;
+    CU(cudaMemcpyAsync(out, d, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return CS_OK;
+}
+static int write_dev(cs_context* c, void* d, const void* in, size_t bytes, size_t expect, const char* what) {
+    if (!c || !in) return CS_ERR_INVALID;
+    if (bytes != expect) return fail(c, CS_ERR_INVALID, std::string(what) + ": bad buffer size");
+    int r = bind(c);
+    if (r) return r;
+    CU(cudaMemcpyAsync(d, in, bytes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return CS_OK;
+}
+int cs_read_transmittance_lut(cs_context* c, uint16_t* out, size_t bytes) {
+    return read_dev(c, c ? c->d_tlut : nullptr, out, bytes, (size_t)CS_TRANSMITTANCE_W * CS_TRANSMITTANCE_H * 8, c && c->have_tlut, "transmittance LUT");
+}
+int cs_read_sky_lut(cs_context* c, uint16_t* out, size_t bytes) {
+    return read_dev(c, c ? c->d_sky : nullptr, out, bytes, (size_t)CS_SKY_LUT_W * CS_SKY_LUT_H * 8, c && c->have_sky, "sky LUT");
+}
+int cs_write_transmittance_lut(cs_context* c, const uint16_t* in, size_t bytes) {
+    int r = write_dev(c, c ? c->d_tlut : nullptr, in, bytes, (size_t)CS_TRANSMITTANCE_W * CS_TRANSMITTANCE_H * 8, "transmittance LUT");
+    if (r == CS_OK) c->have_tlut = true;
+    return r;
+}
+int cs_write_sky_lut(cs_context* c, const uint16_t* in, size_t bytes) {
+    int r = write_dev(c, c ? c->d_sky : nullptr, in, bytes, (size_t)CS_SKY_LUT_W * CS_SKY_LUT_H * 8, "sky LUT");
+    if (r == CS_OK) c->have_sky = true;
+    return r;
+}
+
+int cs_resize(cs_context* c, int w, int h) {
+    if (!c) return CS_ERR_INVALID;
+    if (w < 1 || h < 1 || w > 16384 || h > 16384) return fail(c, CS_ERR_INVALID, "cs_resize: size must be in [1, 16384]");
+    int r = bind(c);
+    if (r) return r;
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->d_image) { cudaFree(c->d_image); c->d_image = nullptr; }
+    c->W = c->H = 0;
+    CU(cudaMalloc(&c->d_image, (size_t)w * h * 8));
+    CU(cudaMemsetAsync(c->d_image, 0, (size_t)w * h * 8, c->stream));
+    c->W = w; c->H = h;
+    return CS_OK;
+}
+int cs_set_march_config(cs_context* c, int p, int cone, int mode) {
+    if (!c) return CS_ERR_INVALID;
+    if (p < 1 || p > 4096 || cone < 0 || cone > 64 || (mode != CS_MODE_FAST && mode != CS_MODE_STRICT))
+        return fail(c, CS_ERR_INVALID, "cs_set_march_config: primary_steps in [1,4096], cone_samples in [0,64], mode FAST|STRICT");
+    c->primary_steps = p; c->cone_samples = cone; c->mode = mode;
+    return CS_OK;
+}
+int cs_set_counters_enabled(cs_context* c, int on) {
+    if (!c) return CS_ERR_INVALID;
+    c->counters_on = on != 0;
+    return CS_OK;
+}
+int cs_get_counters(cs_context* c, cs_counters* out) {
+    if (!c || !out) return CS_ERR_INVALID;
+    int r = bind(c);
+    if (r) return r;
+    unsigned long long h[6];
+    CU(cudaMemcpyAsync(h, c->d_counters, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    out->marched_pixels = h[0]; out->primary_steps = h[1]; out->lit_steps = h[2];
+    out->density_evals = h[3]; out->large_fetches = h[4]; out->small_fetches = h[5];
+    return CS_OK;
+}
+
+int cs_dispatch_clouds(cs_context* c, const cs_cloud_params* P, int gx, int gy) {
+    if (!c || !P) return CS_ERR_INVALID;
+    if (gx < 1 || gy < 1) return fail(c, CS_ERR_INVALID, "cs_dispatch_clouds: group counts must be >= 1");
+    int x0 = (int)P->update_position[0], y0 = (int)P->update_position[1];  // ivec2(params.update_position), clouds.glsl:260
+    return dispatch(c, P, x0, y0, x0 + 8 * gx, y0 + 8 * gy, c->d_image);
+}
+int cs_render_frame(cs_context* c, const cs_cloud_params* P) {
+    if (!c || !P) return CS_ERR_INVALID;
+    return dispatch(c, P, 0, 0, c->W, c->H, c->d_image);
+}
+int cs_render_rows_to(cs_context* c, const cs_cloud_params* P, int r0, int r1, void* out) {
+    if (!c || !P || !out) return CS_ERR_INVALID;
+    return dispatch(c, P, 0, r0, c->W, r1, (uint16_t*)out);
+}
+void* cs_image_device_ptr(cs_context* c) { return c ? c->d_image : nullptr; }
+int cs_read_image(cs_context* c, uint16_t* out, size_t bytes) {
+    if (!c) return CS_ERR_INVALID;
+    return read_dev(c, c->d_image, out, bytes, (size_t)c->W * c->H * 8, c->d_image != nullptr, "output image");
+}
+int cs_render_frame_host(cs_context* c, const cs_cloud_params* P, uint16_t* out, size_t bytes) {
+    if (!c || !P || !out) return CS_ERR_INVALID;
+    if (bytes != (size_t)c->W * c->H * 8) return fail(c, CS_ERR_INVALID, "cs_render_frame_host: bad buffer size");
+    int r = cs_build_sky_lut(c, P->light_direction);
+    if (r) return r;
+    r = dispatch(c, P, 0, 0, c->W, c->H, c->d_image);
+    if (r) return r;
+    CU(cudaMemcpyAsync(out, c->d_image, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return CS_OK;
+}
+int cs_render_sun_batch_to(cs_context* c, const cs_cloud_params* P, const float* suns, int n, void* out) {
+    if (!c || !P || !suns || !out || n < 1) return CS_ERR_INVALID;
+    for (int i = 0; i < n; i++) {
+        cs_cloud_params q = *P;
+        memcpy(q.light_direction, suns + 3 * i, 12);
+        int r = cs_build_sky_lut(c, q.light_direction);
+        if (r) return r;
+        r = dispatch(c, &q, 0, 0, c->W, c->H, (uint16_t*)out + (size_t)i * c->W * c->H * 4);
+        if (r) return r;
+    }
+    return CS_OK;
+}
+int cs_time_render_frame(cs_context* c, const cs_cloud_params* P, int warmup, int iters, float* ms) {
+    if (!c || !P || !ms || iters < 1 || warmup < 0) return CS_ERR_INVALID;
+    int r = bind(c);
+    if (r) return r;
+    for (int i = 0; i < warmup; i++) { r = dispatch(c, P, 0, 0, c->W, c->H, c->d_image); if (r) return r; }
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaEventRecord(e0, c->stream));
+    for (int i = 0; i < iters; i++) { r = dispatch(c, P, 0, 0, c->W, c->H, c->d_image); if (r) break; }
+    cudaEventRecord(e1, c->stream);
+    cudaError_t e = cudaEventSynchronize(e1);
+    float t = 0.0f;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&t, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (r) return r;
+    if (e != cudaSuccess) return cuda_fail(c, e, "cs_time_render_frame");
+    *ms = t / (float)iters;
+    return CS_OK;
+}
+
+}  // extern "C"

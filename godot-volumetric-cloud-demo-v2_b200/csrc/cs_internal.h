@@ -1,0 +1,73 @@
+// Internal types shared by the host-side C++ and the CUDA translation units of
+// libcloudsky_b200.so.  Not part of the public ABI (include/cloudsky.h is).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/cloudsky.h"
+
+namespace cs {
+
+constexpr int kMaxLargeLevels = 8;  // 128 -> 1
+constexpr int kMaxSmallLevels = 6;  // 32 -> 1
+
+// ---- host-side assets (assets.cpp) ----------------------------------------------------------
+struct HostImage {
+    int w = 0, h = 0, ch = 0;  // top-row-first, RGB or RGBA
+    std::vector<uint8_t> px;
+};
+// Decode an RLE / raw true-colour TGA or a BI_RGB BMP.  Returns empty string on success.
+std::string decode_image_file(const char* path, HostImage& out);
+// Slice a (n*slices) x n strip into an n^3 RGBA8 volume, x fastest (texel (x,y,z) = column z*n+x, row y).
+std::string strip_to_volume_rgba(const HostImage& strip, int slices, std::vector<uint8_t>& out, int& n);
+// Expand 3/4-channel interleaved texels to RGBA8 (alpha 255 when absent).
+void expand_rgba(const uint8_t* src, size_t texels, int ch, std::vector<uint8_t>& dst);
+// 2x2x2 box filter, (sum + 4) >> 3, all levels down to 1^3.  levels[0] must hold level 0.
+void build_volume_mips(std::vector<std::vector<uint8_t>>& levels, int n);
+
+// ---- device-side parameter blocks -------------------------------------------------------------
+// Everything the cloud kernels need, passed by value as a __grid_constant__ argument.
+struct CloudLaunch {
+    cs_cloud_params P;        // the push-constant block, verbatim
+    int width, height;        // image size (== P.texture_size)
+    int x0, y0, x1, y1;       // pixel rectangle to render (already clipped)
+    int out_pitch_px;         // row pitch of out, in pixels
+    int primary_steps;        // 128 in the reference
+    int cone_samples;         // 6 in the reference
+    int large_n, large_levels;
+    int small_n, small_levels;
+    int weather_w, weather_h;
+    const uint32_t* large[kMaxLargeLevels];   // RGBA8 texels, x fastest
+    const uint32_t* small[kMaxSmallLevels];   // RGBA8 texels (alpha unused)
+    const uint32_t* weather;                  // RGBA8 texels
+    // packed layouts for the fast kernel (see clouds_fast.cu)
+    const uint32_t* large_pk[kMaxLargeLevels];  // lo16 = R*257 (u16), hi16 = 5G+2B+A (u16, <= 2040)
+    const uint16_t* small_pk[kMaxSmallLevels];  // 5R+2G+B (u16, <= 2040)
+    const uint32_t* weather_pk;                 // lo16 = R (u8 in u16), hi16 = B
+    const uint16_t* sky_lut;                    // half4 200x100
+    const float* frame_consts;                  // FrameConsts written by the prologue kernel
+    uint16_t* out;                              // half4 image
+    unsigned long long* counters;               // 6 x u64 or nullptr
+};
+
+// Pixel-independent values of march()'s prologue (clouds.glsl:149-167), computed once per
+// dispatch by clouds_prologue_kernel and read by every thread.
+struct FrameConsts {
+    float ldir[3];
+    float atmosphere_sun[3];
+    float atmosphere_ambient[3];
+    float atmosphere_ground[3];
+    float hg_g2;  // 0.4 - 1.4 * ldir.y
+    float pad[3];
+};
+
+// kernel launchers (defined in the .cu files) — all asynchronous on `stream`.
+void launch_transmittance_lut(uint16_t* out_half4, void* stream);
+void launch_sky_lut(const uint16_t* transmittance_half4, const float sun_dir[3], uint16_t* out_half4, void* stream);
+void launch_clouds_prologue(const CloudLaunch& L, bool strict, void* stream);
+void launch_clouds_strict(const CloudLaunch& L, void* stream);
+void launch_clouds_fast(const CloudLaunch& L, void* stream);
+
+}  // namespace cs
