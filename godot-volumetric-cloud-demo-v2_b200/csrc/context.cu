@@ -3,9 +3,9 @@
 //
 // HBM layout per context (everything stays resident; the whole working set is ~13 MiB and lives
 // in L2 after the first frame):
-//   large volume : RGBA8 mip chain 128^3 .. 1^3 (9.14 MiB) + packed 2-channel chain for the fast kernel
-//   small volume : RGBA8 mip chain 32^3 .. 1^3 (146 KiB)   + packed 1-channel chain
-//   weather map  : RGBA8 512^2 (1 MiB)                     + packed (R,B) map
+//   large volume : RGBA8 mip chain 128^3 .. 1^3 (9.14 MiB, strict kernel) + fp32 x-pair chain (36.6 MiB, fast kernel)
+//   small volume : RGBA8 mip chain 32^3 .. 1^3 (146 KiB)                  + fp32 xy-quad chain (585 KiB)
+//   weather map  : RGBA8 512^2 (1 MiB)                                    + fp32 x-pair map (4 MiB)
 //   transmittance LUT 256x64 half4, sky LUT 200x100 half4, FrameConsts (64 B)
 //   output image : W*H half4, tightly packed, row 0 = uv.y 0
 #include <cuda_runtime.h>
@@ -32,9 +32,9 @@ struct cs_context {
     uint32_t* d_large[kMaxLargeLevels] = {};
     uint32_t* d_small[kMaxSmallLevels] = {};
     uint32_t* d_weather = nullptr;
-    uint32_t* d_large_pk[kMaxLargeLevels] = {};
-    uint16_t* d_small_pk[kMaxSmallLevels] = {};
-    uint32_t* d_weather_pk = nullptr;
+    float* d_large_f[kMaxLargeLevels] = {};
+    float* d_small_f[kMaxSmallLevels] = {};
+    float* d_weather_f = nullptr;
     std::vector<std::vector<uint8_t>> h_large, h_small;  // host copies of the mip chains (readback / repack)
 
     // LUTs
@@ -76,37 +76,56 @@ int bind(cs_context* c) {
 void free_textures(cs_context* c) {
     for (auto& p : c->d_large) { if (p) cudaFree(p); p = nullptr; }
     for (auto& p : c->d_small) { if (p) cudaFree(p); p = nullptr; }
-    for (auto& p : c->d_large_pk) { if (p) cudaFree(p); p = nullptr; }
-    for (auto& p : c->d_small_pk) { if (p) cudaFree(p); p = nullptr; }
+    for (auto& p : c->d_large_f) { if (p) cudaFree(p); p = nullptr; }
+    for (auto& p : c->d_small_f) { if (p) cudaFree(p); p = nullptr; }
     if (c->d_weather) cudaFree(c->d_weather);
-    if (c->d_weather_pk) cudaFree(c->d_weather_pk);
-    c->d_weather = nullptr; c->d_weather_pk = nullptr;
+    if (c->d_weather_f) cudaFree(c->d_weather_f);
+    c->d_weather = nullptr; c->d_weather_f = nullptr;
     c->have_tex = false;
 }
 
 bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
-// Packed layouts for the fast kernel: only the channel combinations clouds.glsl reads, as exact
-// integers.  large: lo16 = R (0..255), hi16 = 5G + 2B + A (0..2040, = 8 * 255 * fbm, clouds.glsl:118);
-// small: 5R + 2G + B (= 8 * 255 * hfbm, clouds.glsl:133); weather: lo16 = R, hi16 = B (clouds.glsl:121,123).
-void pack_large(const std::vector<uint8_t>& rgba, std::vector<uint32_t>& out) {
-    size_t n = rgba.size() / 4;
-    out.resize(n);
-    for (size_t i = 0; i < n; i++) {
-        uint32_t r = rgba[i * 4], g = rgba[i * 4 + 1], b = rgba[i * 4 + 2], a = rgba[i * 4 + 3];
-        out[i] = r | ((5u * g + 2u * b + a) << 16);
-    }
+// fp32 neighbour-pair layouts for the fast kernel: only the channel combinations clouds.glsl reads
+// (fbm = .625G+.25B+.125A, clouds.glsl:118; hfbm = .625R+.25G+.125B, clouds.glsl:133; weather R and B,
+// clouds.glsl:121,123), each texel stored with its +x (and, for the small volume, +y) neighbours so a
+// filtered fetch is a few aligned 128-bit loads and needs no unpacking.
+inline float un8(uint8_t v) { return (float)v / 255.0f; }
+void pack_large_f(const std::vector<uint8_t>& rgba, int n, std::vector<float>& out) {
+    out.resize((size_t)n * n * n * 4);
+    auto R = [&](size_t i) { return un8(rgba[i * 4]); };
+    auto K = [&](size_t i) { return un8(rgba[i * 4 + 1]) * 0.625f + un8(rgba[i * 4 + 2]) * 0.25f + un8(rgba[i * 4 + 3]) * 0.125f; };
+    for (int z = 0; z < n; z++)
+        for (int y = 0; y < n; y++)
+            for (int x = 0; x < n; x++) {
+                size_t row = ((size_t)z * n + y) * n, i = row + x, j = row + ((x + 1) % n);
+                float* o = &out[i * 4];
+                o[0] = R(i); o[1] = K(i); o[2] = R(j); o[3] = K(j);
+            }
 }
-void pack_small(const std::vector<uint8_t>& rgba, std::vector<uint16_t>& out) {
-    size_t n = rgba.size() / 4;
-    out.resize(n);
-    for (size_t i = 0; i < n; i++) out[i] = (uint16_t)(5u * rgba[i * 4] + 2u * rgba[i * 4 + 1] + rgba[i * 4 + 2]);
+void pack_small_f(const std::vector<uint8_t>& rgba, int n, std::vector<float>& out) {
+    out.resize((size_t)n * n * n * 4);
+    auto Hh = [&](int x, int y, int z) {
+        size_t i = (((size_t)z * n + (y % n)) * n + (x % n));
+        return un8(rgba[i * 4]) * 0.625f + un8(rgba[i * 4 + 1]) * 0.25f + un8(rgba[i * 4 + 2]) * 0.125f;
+    };
+    for (int z = 0; z < n; z++)
+        for (int y = 0; y < n; y++)
+            for (int x = 0; x < n; x++) {
+                float* o = &out[((((size_t)z * n + y) * n) + x) * 4];
+                o[0] = Hh(x, y, z); o[1] = Hh(x + 1, y, z); o[2] = Hh(x, y + 1, z); o[3] = Hh(x + 1, y + 1, z);
+            }
 }
-void pack_weather(const std::vector<uint8_t>& rgba, std::vector<uint32_t>& out) {
-    size_t n = rgba.size() / 4;
-    out.resize(n);
-    for (size_t i = 0; i < n; i++) out[i] = (uint32_t)rgba[i * 4] | ((uint32_t)rgba[i * 4 + 2] << 16);
+void pack_weather_f(const std::vector<uint8_t>& rgba, int w, int h, std::vector<float>& out) {
+    out.resize((size_t)w * h * 4);
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            size_t i = (size_t)y * w + x, j = (size_t)y * w + ((x + 1) % w);
+            float* o = &out[i * 4];
+            o[0] = un8(rgba[i * 4]); o[1] = un8(rgba[i * 4 + 2]); o[2] = un8(rgba[j * 4]); o[3] = un8(rgba[j * 4 + 2]);
+        }
 }
+int ilog2(int v) { int s = 0; while ((1 << s) < v) s++; return s; }
 
 int upload_levels(cs_context* c, const std::vector<uint8_t>& large0, int ln, const std::vector<uint8_t>& small0, int sn,
                   const std::vector<uint8_t>& weather, int ww, int wh) {
@@ -124,27 +143,26 @@ int upload_levels(cs_context* c, const std::vector<uint8_t>& large0, int ln, con
     c->large_n = ln; c->large_levels = (int)c->h_large.size();
     c->small_n = sn; c->small_levels = (int)c->h_small.size();
     c->weather_w = ww; c->weather_h = wh;
-    std::vector<uint32_t> pk;
+    std::vector<float> pk;
     for (int l = 0; l < c->large_levels; l++) {
         CU(cudaMalloc(&c->d_large[l], c->h_large[l].size()));
         CU(cudaMemcpy(c->d_large[l], c->h_large[l].data(), c->h_large[l].size(), cudaMemcpyHostToDevice));
-        pack_large(c->h_large[l], pk);
-        CU(cudaMalloc(&c->d_large_pk[l], pk.size() * 4));
-        CU(cudaMemcpy(c->d_large_pk[l], pk.data(), pk.size() * 4, cudaMemcpyHostToDevice));
+        pack_large_f(c->h_large[l], ln >> l, pk);
+        CU(cudaMalloc(&c->d_large_f[l], pk.size() * 4));
+        CU(cudaMemcpy(c->d_large_f[l], pk.data(), pk.size() * 4, cudaMemcpyHostToDevice));
     }
-    std::vector<uint16_t> pk16;
     for (int l = 0; l < c->small_levels; l++) {
         CU(cudaMalloc(&c->d_small[l], c->h_small[l].size()));
         CU(cudaMemcpy(c->d_small[l], c->h_small[l].data(), c->h_small[l].size(), cudaMemcpyHostToDevice));
-        pack_small(c->h_small[l], pk16);
-        CU(cudaMalloc(&c->d_small_pk[l], pk16.size() * 2 + 16));
-        CU(cudaMemcpy(c->d_small_pk[l], pk16.data(), pk16.size() * 2, cudaMemcpyHostToDevice));
+        pack_small_f(c->h_small[l], sn >> l, pk);
+        CU(cudaMalloc(&c->d_small_f[l], pk.size() * 4));
+        CU(cudaMemcpy(c->d_small_f[l], pk.data(), pk.size() * 4, cudaMemcpyHostToDevice));
     }
     CU(cudaMalloc(&c->d_weather, weather.size()));
     CU(cudaMemcpy(c->d_weather, weather.data(), weather.size(), cudaMemcpyHostToDevice));
-    pack_weather(weather, pk);
-    CU(cudaMalloc(&c->d_weather_pk, pk.size() * 4));
-    CU(cudaMemcpy(c->d_weather_pk, pk.data(), pk.size() * 4, cudaMemcpyHostToDevice));
+    pack_weather_f(weather, ww, wh, pk);
+    CU(cudaMalloc(&c->d_weather_f, pk.size() * 4));
+    CU(cudaMemcpy(c->d_weather_f, pk.data(), pk.size() * 4, cudaMemcpyHostToDevice));
     c->have_tex = true;
     return CS_OK;
 }
@@ -165,9 +183,11 @@ int make_launch(cs_context* c, const cs_cloud_params* P, int x0, int y0, int x1,
     L.large_n = c->large_n; L.large_levels = c->large_levels;
     L.small_n = c->small_n; L.small_levels = c->small_levels;
     L.weather_w = c->weather_w; L.weather_h = c->weather_h;
-    for (int l = 0; l < kMaxLargeLevels; l++) { L.large[l] = c->d_large[l]; L.large_pk[l] = c->d_large_pk[l]; }
-    for (int l = 0; l < kMaxSmallLevels; l++) { L.small[l] = c->d_small[l]; L.small_pk[l] = c->d_small_pk[l]; }
-    L.weather = c->d_weather; L.weather_pk = c->d_weather_pk;
+    for (int l = 0; l < kMaxLargeLevels; l++) { L.large[l] = c->d_large[l]; L.large_f[l] = c->d_large_f[l]; }
+    for (int l = 0; l < kMaxSmallLevels; l++) { L.small[l] = c->d_small[l]; L.small_f[l] = c->d_small_f[l]; }
+    L.weather = c->d_weather; L.weather_f = c->d_weather_f;
+    L.large_shift = ilog2(c->large_n); L.small_shift = ilog2(c->small_n);
+    L.weather_shx = ilog2(c->weather_w); L.weather_shy = ilog2(c->weather_h);
     L.sky_lut = c->d_sky;
     L.frame_consts = c->d_frame_consts;
     L.out = out;
