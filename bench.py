@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py — the measurement contract for the cloud-march hot path.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's algorithm on host cores
+
+Workload (BASELINE.json configs[2], the one `metric` is quoted on): 2048x1024 hemisphere,
+128 primary x 8 light steps (7 cone + 1 distant density evaluations per lit step),
+animated wind: step k renders frame k of the wind animation at absolute time t_k = 1 + k*64/60 s,
+noon sun, demo settings (coverage 0.2, density 0.05).  One "step" = _update_per_frame_data +
+_render_process of the reference (cloud_sky.gd:165-187,234-248): advance the wind offsets on the
+host, rebuild the sky LUT, run the march prologue and the march kernel for the whole image.
+
+Metric: Mray-steps/s = marched pixels (dir.y > 0) x nominal primary steps / seconds / 1e6.
+
+N > 1 (launched under torchrun, one rank per GPU): weak scaling over sun-angle batches
+(BASELINE configs[3]): every rank renders one full frame for its own sun angle straight into its
+slice of the gathered [N, H, W, 4] fp16 tensor, followed by ONE NCCL all-gather of the finished
+textures over NVLink; value = N frames' ray-steps / max-over-ranks device time.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+W, H, PRIMARY, LIGHT = 2048, 1024, 128, 8
+CONE = LIGHT - 1
+METRIC = "Mray-steps/sec, 2048x1024 hemisphere @128x8 steps; achieved HBM GB/s vs peak"
+UNIT = "Mray-steps/s"
+WORKLOAD = "C3: 2048x1024 hemisphere, 128 primary / 8 light (7 cone + 1 distant) steps, animated wind, noon sun"
+L2_FLUSH_BYTES = 256 << 20
+
+
+def frame_time(k):
+    return 1.0 + k * (64.0 / 60.0)
+
+
+def sun_for_rank(rank, world):
+    if world == 1:
+        return (0.0, 1.0, 0.0)
+    th = math.pi * (rank + 0.5) / world  # dir_k = (cos th_k, sin th_k, 0)
+    return (math.cos(th), math.sin(th), 0.0)
+
+
+def frame_params(lib, k, sun):
+    """Settings -> FrameData -> push constants for animation frame k (host logic of cloud_sky.gd)."""
+    s = lib.settings_demo()
+    st = lib.frame_state_init()
+    st.light_direction[:] = list(sun)
+    for j in range(k + 1):  # integrate the wind offsets frame by frame like the running demo does
+        lib.frame_advance(st, s, frame_time(j))
+    return lib.fill_cloud_params(s, st, W, H)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sm = sorted(int(r[1]) for r in self.rows if len(r) > 2 and r[1].isdigit())
+        mx = max([int(r[2]) for r in self.rows if len(r) > 2 and r[2].isdigit()], default=None)
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        # samples taken while the SMs were busy have the highest clocks; report the median of the upper half
+        busy = sm[len(sm) // 2:] if sm else []
+        return {"sm_mhz": busy[len(busy) // 2] if busy else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_library(cs):
+    """The CPU oracle (test infrastructure): only used for the cpu_baseline leg and --impl reference."""
+    path = os.path.join(ROOT, "oracle", "libcloudsky_oracle.so")
+    if not os.path.exists(path):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-s"])
+    return cs.Library(path)
+
+
+def cpu_rows_sample(cs, textures, params, sun, target_seconds, threads):
+    """Times the oracle on evenly spaced row bands of the SAME frame (the whole frame when it fits the
+    time budget); returns (Mray-steps/s, sample description, seconds)."""
+    import numpy as np
+    ora = oracle_library(cs)
+    ctx = ora.context(0)
+    ctx.set_threads(threads)
+    ctx.upload_textures(*textures)
+    ctx.build_transmittance_lut()
+    ctx.build_sky_lut(sun)
+    ctx.resize(W, H)
+    ctx.set_march_config(PRIMARY, CONE)
+    buf = np.zeros((H, W, 4), np.float16)
+    band = min(H, max(threads, 8))  # rows per call: the oracle parallelises over the rows of one call
+    t0 = time.perf_counter()
+    ctx.render_rows_to(params, H // 3, H // 3 + band, buf.ctypes.data)  # calibration band, not part of the sample
+    t_band = time.perf_counter() - t0
+    max_bands = H // band
+    n_bands = max(1, min(max_bands, int(target_seconds / max(t_band, 1e-6))))
+    steps = 0
+    t0 = time.perf_counter()
+    if n_bands == max_bands:
+        ctx.render_rows_to(params, 0, H, buf.ctypes.data)
+        steps = ctx.get_counters().primary_steps
+        desc = f"the whole 2048x1024 frame"
+    else:
+        pitch = H / n_bands
+        for i in range(n_bands):
+            r0 = min(H - band, int(i * pitch + (pitch - band) / 2))
+            ctx.render_rows_to(params, r0, r0 + band, buf.ctypes.data)
+            steps += ctx.get_counters().primary_steps
+        desc = f"{n_bands} evenly spaced bands of {band} rows ({n_bands * band} of {H} rows) of the same 2048x1024 frame"
+    sec = time.perf_counter() - t0
+    ctx.close()
+    desc += f", {PRIMARY}/{LIGHT} steps, scalar fp32 C++ oracle (-O2 -ffp-contract=off), {threads} threads"
+    return steps / sec / 1e6, desc, sec
+
+
+def run_reference(args):
+    """--impl reference: the reference's own algorithm (the oracle port: nothing in this container or on
+    the GPU box can execute Godot/GLSL) on all host cores, same config/metric, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import cloudsky_b200 as cs
+    from cloudsky_b200 import assets
+    large, small, weather, desc = assets.load_default_textures()
+    threads = os.cpu_count() or 1
+    ora = oracle_library(cs)
+    vals, secs = [], []
+    sample = ""
+    for k in range(args.warmup + args.steps):
+        p = frame_params(ora, k % 16, (0.0, 1.0, 0.0))
+        v, sample, sec = cpu_rows_sample(cs, (large, small, weather), p, (0.0, 1.0, 0.0), 4.0 if k >= args.warmup else 1.0, threads)
+        if k >= args.warmup:
+            vals.append(v); secs.append(sec)
+    value = sum(vals) / len(vals)
+    line = {"impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(1e3 * sum(secs) / len(secs), 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": desc,
+            "config": {"workload": WORKLOAD, "width": W, "height": H, "primary_steps": PRIMARY, "light_steps": LIGHT},
+            "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy bandwidth)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the march kernel from the committed `ncu --set full` capture, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_latest.json")) as f:
+            d = json.load(f)
+        return d.get("dram_bytes_per_launch"), d.get("source")
+    except Exception:
+        return None, None
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import cloudsky_b200 as cs
+    from cloudsky_b200 import assets
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    lib = cs.load_product()
+    large, small, weather, desc = assets.load_default_textures()
+    ctx = lib.context(local)
+    stream = torch.cuda.Stream()  # an explicit stream: torch's default stream is handle 0, which cs_set_stream reads as "own stream"
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
+    ctx.upload_textures(large, small, weather)
+    ctx.build_transmittance_lut()
+    ctx.resize(W, H)
+    ctx.set_march_config(PRIMARY, CONE, cs.MODE_FAST)
+    sun = sun_for_rank(rank, world)
+    gathered = torch.zeros((world, H, W, 4), dtype=torch.float16, device="cuda")
+    mine = gathered[rank]
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
+    params = [frame_params(lib, k % 16, sun) for k in range(16)]
+
+    # work counters of frame 0 (deterministic; measured outside the timed region with the instrumented kernel)
+    ctx.build_sky_lut(sun)
+    ctx.set_counters_enabled(True)
+    ctx.render_frame(params[0])
+    counters = ctx.get_counters().as_dict()
+    ctx.set_counters_enabled(False)
+
+    def step(k):
+        p = params[k % 16]
+        ctx.build_sky_lut(sun)                       # sky_lut.update_lut (cloud_sky.gd:187)
+        ctx.render_rows_to(p, 0, H, mine.data_ptr())  # prologue + march into this rank's slice
+        if dist is not None:
+            dist.all_gather_into_tensor(gathered.view(-1), mine.reshape(-1))
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    for k in range(args.warmup):
+        step(k)
+    torch.cuda.synchronize()
+    if rank == 0:
+        time.sleep(0.3)   # let nvidia-smi come up, then drop what it saw during warm-up / idle
+        sampler.rows.clear()
+    ctx.set_kernel_timing(True)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.zero_()  # evict L2 between timed steps (outside the per-step event pair)
+        ev[k][0].record(stream)
+        step(args.warmup + k)
+        ev[k][1].record(stream)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop() if rank == 0 else None
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    kt = ctx.read_kernel_timings()
+    ctx.set_kernel_timing(False)
+    if dist is not None:
+        t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms = float(t.item())
+
+    ray_steps_per_frame = counters["marched_pixels"] * PRIMARY
+    value = world * ray_steps_per_frame * args.steps / (dev_ms * 1e-3) / 1e6
+    ms_per_step = dev_ms / args.steps
+
+    # end-to-end through the C-ABI with HOST buffers: params from host memory, result into pinned host memory
+    e2e = None
+    if True:
+        host = torch.empty((H, W, 4), dtype=torch.float16).pin_memory()
+        for k in range(min(3, args.warmup)):
+            ctx.render_frame_host(params[k % 16], out_ptr=host.data_ptr())
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            ctx.render_frame_host(params[(args.warmup + k) % 16], out_ptr=host.data_ptr())  # sky LUT + march + D2H, synchronous
+        e2e_s = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        assert torch.isfinite(host.float()).all()
+        e2e = {"value": round(world * ray_steps_per_frame * args.steps / e2e_s / 1e6, 1), "unit": UNIT,
+               "h2d_bytes_per_step": 112 + 12, "d2h_bytes_per_step": W * H * 8,
+               "note": "cs_render_frame_host: push constants from host, sky LUT + prologue + march, 16 MiB RGBA16F result copied to pinned host memory, synchronous per step"}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = measured_peak()
+    alg_bytes = 80 * counters["density_evals"] + 8 * W * H  # 80 B per density evaluation + 8 B per pixel
+    march_ms = kt["march_ms"] / max(1, kt["march_launches"])
+    achieved = alg_bytes / (march_ms * 1e-3) / 1e9
+    traffic, traffic_src = ncu_traffic()
+    roofline = {"bound": "hbm", "kernel": "clouds_fast_kernel", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                "kernel_ms": round(march_ms, 4), "algorithmic_bytes_per_launch": alg_bytes,
+                "note": "algorithmic bytes = 80 B x executed density evaluations + 8 B x pixels (SURVEY 8(d)); the texel working set is L1/L2-resident, "
+                        "so DRAM traffic is far below this figure and frac can exceed 1"}
+    cpu_threads = os.cpu_count() or 1
+    cpu_v, cpu_sample, _ = cpu_rows_sample(cs, (large, small, weather), params[0], sun, 12.0, cpu_threads) if world == 1 else (None, None, None)
+    line = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": desc,
+            "config": {"workload": WORKLOAD, "width": W, "height": H, "primary_steps": PRIMARY, "light_steps": LIGHT, "cone_samples": CONE,
+                       "l2": f"flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB memset outside the per-step event pairs)",
+                       "parallelism": "1 GPU" if world == 1 else f"{world} GPUs: one sun-angle frame per rank + NCCL all-gather of the finished textures",
+                       "lit_fraction": round(counters["lit_steps"] / counters["primary_steps"], 4),
+                       "density_evals_per_frame": counters["density_evals"], "marched_pixels": counters["marched_pixels"]},
+            "roofline": roofline, "e2e": e2e, "gpu_launches": 3 * args.steps,
+            "kernels": {"march_ms_avg": round(march_ms, 4), "sky_lut_ms_avg": round(kt["sky_ms"] / max(1, kt["sky_launches"]), 4)},
+            "gevals_per_s": round(world * counters["density_evals"] * args.steps / (dev_ms * 1e-3) / 1e9, 2),
+            "wall_ms_per_step_incl_flush": round(1e3 * t_wall / args.steps, 3), "clocks": clocks}
+    if cpu_v is not None:
+        line["cpu_baseline"] = {"value": round(cpu_v, 3), "unit": UNIT, "cores": cpu_threads, "kind": "port", "sample": cpu_sample}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

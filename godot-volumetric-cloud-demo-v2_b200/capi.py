@@ -142,6 +142,8 @@ _PROTOTYPES = {
     "cs_render_frame_host": (C.c_int, [_P, C.POINTER(CloudParams), _P, C.c_size_t]),
     "cs_render_sun_batch_to": (C.c_int, [_P, C.POINTER(CloudParams), C.POINTER(C.c_float), C.c_int, _P]),
     "cs_time_render_frame": (C.c_int, [_P, C.POINTER(CloudParams), C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    "cs_set_kernel_timing": (C.c_int, [_P, C.c_int]),
+    "cs_read_kernel_timings": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "cs_settings_default": (None, [C.POINTER(SkySettings)]),
     "cs_settings_demo": (None, [C.POINTER(SkySettings)]),
     "cs_frame_state_init": (None, [C.POINTER(FrameState)]),
@@ -370,6 +372,15 @@ class Context:
     def render_sun_batch_to(self, params: CloudParams, sun_dirs: np.ndarray, device_ptr: int) -> None:
         s = np.ascontiguousarray(sun_dirs, dtype=np.float32).reshape(-1, 3)
         self._ck(self.lib.dll.cs_render_sun_batch_to(self._h, C.byref(params), s.ctypes.data_as(C.POINTER(C.c_float)), s.shape[0], _P(device_ptr)))
+
+    def set_kernel_timing(self, on: bool) -> None:
+        self._ck(self.lib.dll.cs_set_kernel_timing(self._h, int(on)))
+
+    def read_kernel_timings(self) -> dict:
+        m, s = C.c_float(), C.c_float()
+        nm, ns = C.c_int(), C.c_int()
+        self._ck(self.lib.dll.cs_read_kernel_timings(self._h, C.byref(m), C.byref(nm), C.byref(s), C.byref(ns)))
+        return {"march_ms": float(m.value), "march_launches": nm.value, "sky_ms": float(s.value), "sky_launches": ns.value}
 
     def time_render_frame(self, params: CloudParams, warmup: int, iters: int) -> float:
         ms = C.c_float()

@@ -51,6 +51,11 @@ struct cs_context {
     int primary_steps = CS_REF_PRIMARY_STEPS, cone_samples = CS_REF_CONE_SAMPLES, mode = CS_MODE_FAST;
     bool counters_on = false;
     unsigned long long* d_counters = nullptr;
+
+    // optional per-kernel event timing (cs_set_kernel_timing)
+    bool timing_on = false;
+    std::vector<cudaEvent_t> ev_march, ev_sky;  // begin/end pairs, recycled
+    size_t n_march = 0, n_sky = 0;              // pairs recorded since the last read
 };
 
 namespace {
@@ -88,8 +93,8 @@ bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 // fp32 neighbour-pair layouts for the fast kernel: only the channel combinations clouds.glsl reads
 // (fbm = .625G+.25B+.125A, clouds.glsl:118; hfbm = .625R+.25G+.125B, clouds.glsl:133; weather R and B,
-// clouds.glsl:121,123), each texel stored with its +x (and, for the small volume, +y) neighbours so a
-// filtered fetch is a few aligned 128-bit loads and needs no unpacking.
+// clouds.glsl:121,123), each texel stored with the deltas to its +x (and, for the small volume, +y/+xy) neighbours so a
+// filtered fetch is a few aligned 128-bit loads, needs no unpacking, and an x-lerp is one FFMA.
 inline float un8(uint8_t v) { return (float)v / 255.0f; }
 void pack_large_f(const std::vector<uint8_t>& rgba, int n, std::vector<float>& out) {
     out.resize((size_t)n * n * n * 4);
@@ -100,7 +105,7 @@ void pack_large_f(const std::vector<uint8_t>& rgba, int n, std::vector<float>& o
             for (int x = 0; x < n; x++) {
                 size_t row = ((size_t)z * n + y) * n, i = row + x, j = row + ((x + 1) % n);
                 float* o = &out[i * 4];
-                o[0] = R(i); o[1] = K(i); o[2] = R(j); o[3] = K(j);
+                o[0] = R(i); o[1] = K(i); o[2] = R(j) - R(i); o[3] = K(j) - K(i);
             }
 }
 void pack_small_f(const std::vector<uint8_t>& rgba, int n, std::vector<float>& out) {
@@ -113,7 +118,8 @@ void pack_small_f(const std::vector<uint8_t>& rgba, int n, std::vector<float>& o
         for (int y = 0; y < n; y++)
             for (int x = 0; x < n; x++) {
                 float* o = &out[((((size_t)z * n + y) * n) + x) * 4];
-                o[0] = Hh(x, y, z); o[1] = Hh(x + 1, y, z); o[2] = Hh(x, y + 1, z); o[3] = Hh(x + 1, y + 1, z);
+                float h00 = Hh(x, y, z), h10 = Hh(x + 1, y, z), h01 = Hh(x, y + 1, z), h11 = Hh(x + 1, y + 1, z);
+                o[0] = h00; o[1] = h10 - h00; o[2] = h01 - h00; o[3] = (h11 - h01) - (h10 - h00);
             }
 }
 void pack_weather_f(const std::vector<uint8_t>& rgba, int w, int h, std::vector<float>& out) {
@@ -122,7 +128,7 @@ void pack_weather_f(const std::vector<uint8_t>& rgba, int w, int h, std::vector<
         for (int x = 0; x < w; x++) {
             size_t i = (size_t)y * w + x, j = (size_t)y * w + ((x + 1) % w);
             float* o = &out[i * 4];
-            o[0] = un8(rgba[i * 4]); o[1] = un8(rgba[i * 4 + 2]); o[2] = un8(rgba[j * 4]); o[3] = un8(rgba[j * 4 + 2]);
+            o[0] = un8(rgba[i * 4]); o[1] = un8(rgba[i * 4 + 2]); o[2] = un8(rgba[j * 4]) - o[0]; o[3] = un8(rgba[j * 4 + 2]) - o[1];
         }
 }
 int ilog2(int v) { int s = 0; while ((1 << s) < v) s++; return s; }
@@ -195,6 +201,16 @@ int make_launch(cs_context* c, const cs_cloud_params* P, int x0, int y0, int x1,
     return CS_OK;
 }
 
+// Record one side of an event pair (pairs are created on demand and reused after each read).
+void timing_mark(cs_context* c, std::vector<cudaEvent_t>& evs, size_t pair, int side) {
+    while (evs.size() < 2 * (pair + 1)) {
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        evs.push_back(e);
+    }
+    cudaEventRecord(evs[2 * pair + side], c->stream);
+}
+
 // prologue + march for one rectangle, asynchronous on c->stream
 int dispatch(cs_context* c, const cs_cloud_params* P, int x0, int y0, int x1, int y1, uint16_t* out) {
     if (!c || !P) return CS_ERR_INVALID;
@@ -206,8 +222,10 @@ int dispatch(cs_context* c, const cs_cloud_params* P, int x0, int y0, int x1, in
     if (L.x1 <= L.x0 || L.y1 <= L.y0) return CS_OK;
     if (L.counters) CU(cudaMemsetAsync(c->d_counters, 0, 6 * sizeof(unsigned long long), c->stream));
     launch_clouds_prologue(L, c->mode == CS_MODE_STRICT, c->stream);
+    if (c->timing_on) timing_mark(c, c->ev_march, c->n_march, 0);
     if (c->mode == CS_MODE_STRICT) launch_clouds_strict(L, c->stream);
     else launch_clouds_fast(L, c->stream);
+    if (c->timing_on) timing_mark(c, c->ev_march, c->n_march++, 1);
     CU(cudaGetLastError());
     return CS_OK;
 }
@@ -253,6 +271,8 @@ void cs_destroy(cs_context* c) {
     if (c->d_frame_consts) cudaFree(c->d_frame_consts);
     if (c->d_counters) cudaFree(c->d_counters);
     if (c->d_image) cudaFree(c->d_image);
+    for (auto e : c->ev_march) cudaEventDestroy(e);
+    for (auto e : c->ev_sky) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -350,7 +370,9 @@ int cs_build_sky_lut(cs_context* c, const float sun[3]) {
     if (!c->have_tlut) return fail(c, CS_ERR_NOT_READY, "Attempting to update uninitialized sky lut (build the transmittance LUT first)");
     int r = bind(c);
     if (r) return r;
+    if (c->timing_on) timing_mark(c, c->ev_sky, c->n_sky, 0);
     launch_sky_lut(c->d_tlut, sun, c->d_sky, c->stream);
+    if (c->timing_on) timing_mark(c, c->ev_sky, c->n_sky++, 1);
     CU(cudaGetLastError());
     c->have_sky = true;
     return CS_OK;
@@ -426,6 +448,28 @@ int cs_get_counters(cs_context* c, cs_counters* out) {
     CU(cudaStreamSynchronize(c->stream));
     out->marched_pixels = h[0]; out->primary_steps = h[1]; out->lit_steps = h[2];
     out->density_evals = h[3]; out->large_fetches = h[4]; out->small_fetches = h[5];
+    return CS_OK;
+}
+
+int cs_set_kernel_timing(cs_context* c, int on) {
+    if (!c) return CS_ERR_INVALID;
+    int r = bind(c);
+    if (r) return r;
+    CU(cudaStreamSynchronize(c->stream));
+    c->timing_on = on != 0;
+    c->n_march = c->n_sky = 0;
+    return CS_OK;
+}
+int cs_read_kernel_timings(cs_context* c, float* march_ms, int* n_march, float* sky_ms, int* n_sky) {
+    if (!c || !march_ms || !n_march || !sky_ms || !n_sky) return CS_ERR_INVALID;
+    int r = bind(c);
+    if (r) return r;
+    CU(cudaStreamSynchronize(c->stream));
+    float sm = 0.0f, ss = 0.0f, t = 0.0f;
+    for (size_t i = 0; i < c->n_march; i++) { CU(cudaEventElapsedTime(&t, c->ev_march[2 * i], c->ev_march[2 * i + 1])); sm += t; }
+    for (size_t i = 0; i < c->n_sky; i++) { CU(cudaEventElapsedTime(&t, c->ev_sky[2 * i], c->ev_sky[2 * i + 1])); ss += t; }
+    *march_ms = sm; *n_march = (int)c->n_march; *sky_ms = ss; *n_sky = (int)c->n_sky;
+    c->n_march = c->n_sky = 0;
     return CS_OK;
 }
 

@@ -44,9 +44,9 @@ struct CloudLaunch {
     const uint32_t* weather;                  // RGBA8 texels
     // fp32 neighbour-pair layouts for the fast kernel (see clouds_fast.cu)
     int large_shift, small_shift, weather_shx, weather_shy;  // log2 of the level-0 edges
-    const float* large_f[kMaxLargeLevels];  // float4 {R, fbm, R(x+1), fbm(x+1)} per texel
-    const float* small_f[kMaxSmallLevels];  // float4 {h(x,y), h(x+1,y), h(x,y+1), h(x+1,y+1)} per texel
-    const float* weather_f;                 // float4 {type, coverage, type(x+1), coverage(x+1)} per texel
+    const float* large_f[kMaxLargeLevels];  // float4 {R, fbm, dR, dfbm} (delta to texel x+1) per texel
+    const float* small_f[kMaxSmallLevels];  // float4 {h, dx, dy, dxy} bilinear deltas per texel
+    const float* weather_f;                 // float4 {type, coverage, dtype, dcoverage} per texel
     const uint16_t* sky_lut;                    // half4 200x100
     const float* frame_consts;                  // FrameConsts written by the prologue kernel
     uint16_t* out;                              // half4 image

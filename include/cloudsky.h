@@ -214,6 +214,13 @@ int cs_render_sun_batch_to(cs_context* ctx, const cs_cloud_params* params, const
 int cs_time_render_frame(cs_context* ctx, const cs_cloud_params* params, int warmup, int iters,
                          float* out_ms_avg);
 
+/* Per-kernel device timing: when enabled, every sky-LUT build and every cloud-march launch is
+ * bracketed by CUDA events on the context's stream.  cs_read_kernel_timings synchronises, returns
+ * the summed milliseconds and launch counts since the last read, and resets them. */
+int cs_set_kernel_timing(cs_context* ctx, int enabled);
+int cs_read_kernel_timings(cs_context* ctx, float* march_ms_sum, int* march_launches, float* sky_ms_sum,
+                           int* sky_launches);
+
 /* ---- host-side parameter logic (pure CPU, no context) ------------------------------------ */
 
 /* Script defaults of cloud_sky.gd:4-50 (coverage 0.25, white ground, 768, 64 frames). */

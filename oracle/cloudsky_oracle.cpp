@@ -790,6 +790,9 @@ int cs_time_render_frame(cs_context* c, const cs_cloud_params*, int, int, float*
     return fail(c, CS_ERR_UNSUPPORTED, "device timing is CUDA-only");
 }
 
+int cs_set_kernel_timing(cs_context* c, int) { return fail(c, CS_ERR_UNSUPPORTED, "device timing is CUDA-only"); }
+int cs_read_kernel_timings(cs_context* c, float*, int*, float*, int*) { return fail(c, CS_ERR_UNSUPPORTED, "device timing is CUDA-only"); }
+
 // ---- host-side parameter logic (cloud_sky.gd) -------------------------------------------------
 void cs_settings_default(cs_sky_settings* s) {  // cloud_sky.gd:4-50
     s->wind_direction = 0.0f; s->wind_speed = 1.0f; s->density = 0.05f; s->cloud_coverage = 0.25f; s->time_offset = 0.0f;

@@ -10,7 +10,10 @@ def main():
     lib = cs.load_product()
     large, small, weather, desc = assets.load_default_textures()
     res = []
-    for (W, H, P, cone, cov) in [(2048, 1024, 128, 6, 0.2), (2048, 1024, 128, 7, 0.2), (2048, 1024, 128, 7, 1.0), (1024, 512, 64, 5, 0.2)]:
+    cfgs = [(2048, 1024, 128, 6, 0.2), (2048, 1024, 128, 7, 0.2), (2048, 1024, 128, 7, 1.0), (1024, 512, 64, 5, 0.2)]
+    if "--only" in sys.argv:
+        cfgs = [cfgs[int(sys.argv[sys.argv.index("--only") + 1])]]
+    for (W, H, P, cone, cov) in cfgs:
         ctx = lib.context(0)
         ctx.upload_textures(large, small, weather)
         ctx.build_transmittance_lut(); ctx.build_sky_lut((0, 1, 0)); ctx.resize(W, H)
