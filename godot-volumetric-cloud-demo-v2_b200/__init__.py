@@ -9,5 +9,7 @@ from . import capi  # noqa: F401
 from .capi import (CloudParams, CloudSkyError, Context, Counters, FrameState, Library, SkySettings,  # noqa: F401
                    MODE_FAST, MODE_STRICT, load_product)
 
-__all__ = ["capi", "CloudParams", "CloudSkyError", "Context", "Counters", "FrameState", "Library", "SkySettings",
+from .sky import CloudSky, DirectionalLight, SkyLUT, TransmittanceLUT  # noqa: F401,E402
+
+__all__ = ["CloudSky", "DirectionalLight", "SkyLUT", "TransmittanceLUT", "capi", "CloudParams", "CloudSkyError", "Context", "Counters", "FrameState", "Library", "SkySettings",
            "MODE_FAST", "MODE_STRICT", "load_product"]

@@ -852,4 +852,51 @@ void cs_next_update_position(int* x, int* y, int region, int ts) {  // cloud_sky
     if (*y >= ts) { *x = 0; *y = 0; }
 }
 
+
+// ---- oracle-only probes for the known-answer tests (tests/test_oracle_known_answers.py) --------
+// Not part of include/cloudsky.h; they expose the internal functions of the restatement so that
+// each can be pinned against an analytic answer derived from the shader source.
+float cso_intersect_sphere(const float dir[3], float r) { return intersectSphere({0.0f, g_radius, 0.0f}, {dir[0], dir[1], dir[2]}, r); }
+float cso_hash(const float p[3]) { return hash3({p[0], p[1], p[2]}); }
+float cso_henyey_greenstein(float c, float g) { return henyey_greenstein(c, g); }
+float cso_remap(float v, float a, float b, float c, float d) { return remap(v, a, b, c, d); }
+float cso_height_fraction(float r) { return GetHeightFractionForPoint(r); }
+float cso_density_height_gradient(float hf, float type) { return densityHeightGradient(hf, type); }
+void cso_oct_to_dir(float u, float v, float out[3]) { V3 n = oct_to_vec3({u, v}); out[0] = n.x; out[1] = n.z; out[2] = n.y; }
+uint16_t cso_f32_to_f16(float f) { return f32_to_f16(f); }
+float cso_f16_to_f32(uint16_t h) { return f16_to_f32(h); }
+int cso_sample_volume(cs_context* c, int which, const float s[3], float lod, float out[4]) {
+    if (!c || !c->have_tex) return CS_ERR_NOT_READY;
+    V4 v = sample_volume(which == 0 ? c->large : c->small, {s[0], s[1], s[2]}, lod);
+    out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+    return CS_OK;
+}
+int cso_sample_weather(cs_context* c, float u, float v, float out[3]) {
+    if (!c || !c->have_tex) return CS_ERR_NOT_READY;
+    V3 w = sample_weather(c->weather, {u, v});
+    out[0] = w.x; out[1] = w.y; out[2] = w.z;
+    return CS_OK;
+}
+int cso_sample_lut(cs_context* c, int which, float u, float v, float out[4]) {
+    if (!c) return CS_ERR_INVALID;
+    V4 t = which == 0 ? sample_lut(c->tlut.data(), CS_TRANSMITTANCE_W, CS_TRANSMITTANCE_H, u, v) : sample_lut(c->skylut.data(), CS_SKY_LUT_W, CS_SKY_LUT_H, u, v);
+    out[0] = t.x; out[1] = t.y; out[2] = t.z; out[3] = t.w;
+    return CS_OK;
+}
+float cso_density(cs_context* c, const cs_cloud_params* P, const float p[3], const float weather[3], float mip) {
+    if (!c || !c->have_tex) return -1.0f;
+    CloudCtx cc{&c->large, &c->small, &c->weather, c->skylut.data(), *P, c->primary_steps, c->cone_samples};
+    Tally tl;
+    return density(cc, {p[0], p[1], p[2]}, {weather[0], weather[1], weather[2]}, mip, tl);
+}
+// start distance, end distance, step length and first marched position for a view direction (sky(), clouds.glsl:218-237)
+void cso_ray_setup(const float dir[3], int steps, float out[6]) {
+    V3 d = {dir[0], dir[1], dir[2]}, cam = {0.0f, g_radius, 0.0f};
+    float t0 = intersectSphere(cam, d, sky_b_radius), t1 = intersectSphere(cam, d, sky_t_radius);
+    V3 start = cam + d * t0, end = cam + d * t1;
+    float shell = length3(end - start);
+    V3 rs = (d * shell) / (float)steps;
+    out[0] = t0; out[1] = t1; out[2] = shell; out[3] = length3(rs); out[4] = hash3(start * 10.0f); out[5] = length3(start);
+}
+
 }  // extern "C"
