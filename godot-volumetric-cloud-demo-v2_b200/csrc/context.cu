@@ -1,11 +1,11 @@
 // libcloudsky_b200.so — context management and the C-ABI of include/cloudsky.h on top of the
 // sm_100a kernels (lut_kernels.cu, clouds_strict.cu, clouds_fast.cu).
 //
-// HBM layout per context (everything stays resident; the whole working set is ~13 MiB and lives
-// in L2 after the first frame):
-//   large volume : RGBA8 mip chain 128^3 .. 1^3 (9.14 MiB, strict kernel) + fp32 x-pair chain (36.6 MiB, fast kernel)
-//   small volume : RGBA8 mip chain 32^3 .. 1^3 (146 KiB)                  + fp32 xy-quad chain (585 KiB)
-//   weather map  : RGBA8 512^2 (1 MiB)                                    + fp32 x-pair map (4 MiB)
+// HBM layout per context (everything stays resident; the part of it a frame touches, ~40 MiB, lives in
+// L2 after the first frame):
+//   large volume : RGBA8 mip chain 128^3 .. 1^3 (9.14 MiB, strict kernel) + 64-B coefficient records (146 MiB, fast kernel)
+//   small volume : RGBA8 mip chain 32^3 .. 1^3 (146 KiB)                  + 32-B coefficient records (1.14 MiB)
+//   weather map  : RGBA8 512^2 (1 MiB)                                    + 32-B coefficient records (8 MiB)
 //   transmittance LUT 256x64 half4, sky LUT 200x100 half4, FrameConsts (64 B)
 //   output image : W*H half4, tightly packed, row 0 = uv.y 0
 #include <cuda_runtime.h>
@@ -29,6 +29,7 @@ struct cs_context {
     // textures
     bool have_tex = false;
     int large_n = 0, large_levels = 0, small_n = 0, small_levels = 0, weather_w = 0, weather_h = 0;
+    int weather_type_hi = 0;
     uint32_t* d_large[kMaxLargeLevels] = {};
     uint32_t* d_small[kMaxSmallLevels] = {};
     uint32_t* d_weather = nullptr;
@@ -91,44 +92,68 @@ void free_textures(cs_context* c) {
 
 bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
-// fp32 neighbour-pair layouts for the fast kernel: only the channel combinations clouds.glsl reads
-// (fbm = .625G+.25B+.125A, clouds.glsl:118; hfbm = .625R+.25G+.125B, clouds.glsl:133; weather R and B,
-// clouds.glsl:121,123), each texel stored with the deltas to its +x (and, for the small volume, +y/+xy) neighbours so a
-// filtered fetch is a few aligned 128-bit loads, needs no unpacking, and an x-lerp is one FFMA.
+// Interpolation-coefficient records for the fast kernel.  Only the channel combinations clouds.glsl reads
+// are kept (fbm = .625G+.25B+.125A, clouds.glsl:118; hfbm = .625R+.25G+.125B, clouds.glsl:133; weather R and
+// B, clouds.glsl:121,123).  Each texel (x,y,z) stores the 8 coefficients of the trilinear polynomial over the
+// cell [x,x+1]x[y,y+1]x[z,z+1] (REPEAT wrap baked in):
+//     v(fx,fy,fz) = c0 + fx c1 + fy (c2 + fx c3) + fz (c4 + fx c5 + fy (c6 + fx c7))
+// so one filtered fetch reads ONE aligned record (one 128-byte line), needs a single address, no unpacking
+// and 7 FFMAs per channel.  large: 64 B per texel (R coefficients, then fbm), small: 32 B, weather (bilinear,
+// 4 coefficients per channel): 32 B.
 inline float un8(uint8_t v) { return (float)v / 255.0f; }
+
+template <class F>
+void trilinear_coeffs(F v, int n, int x, int y, int z, float* c) {
+    int x1 = (x + 1) % n, y1 = (y + 1) % n, z1 = (z + 1) % n;
+    float v000 = v(x, y, z), v100 = v(x1, y, z), v010 = v(x, y1, z), v110 = v(x1, y1, z);
+    float v001 = v(x, y, z1), v101 = v(x1, y, z1), v011 = v(x, y1, z1), v111 = v(x1, y1, z1);
+    c[0] = v000;
+    c[1] = v100 - v000;
+    c[2] = v010 - v000;
+    c[3] = (v110 - v010) - c[1];
+    c[4] = v001 - v000;
+    c[5] = (v101 - v001) - c[1];
+    c[6] = (v011 - v001) - c[2];
+    c[7] = ((v111 - v011) - (v101 - v001)) - c[3];
+}
 void pack_large_f(const std::vector<uint8_t>& rgba, int n, std::vector<float>& out) {
-    out.resize((size_t)n * n * n * 4);
-    auto R = [&](size_t i) { return un8(rgba[i * 4]); };
-    auto K = [&](size_t i) { return un8(rgba[i * 4 + 1]) * 0.625f + un8(rgba[i * 4 + 2]) * 0.25f + un8(rgba[i * 4 + 3]) * 0.125f; };
+    std::vector<float> R((size_t)n * n * n), K(R.size());
+    for (size_t i = 0; i < R.size(); i++) {
+        R[i] = un8(rgba[i * 4]);
+        K[i] = un8(rgba[i * 4 + 1]) * 0.625f + un8(rgba[i * 4 + 2]) * 0.25f + un8(rgba[i * 4 + 3]) * 0.125f;
+    }
+    out.resize(R.size() * 16);
+    auto fr = [&](int x, int y, int z) { return R[((size_t)z * n + y) * n + x]; };
+    auto fk = [&](int x, int y, int z) { return K[((size_t)z * n + y) * n + x]; };
     for (int z = 0; z < n; z++)
         for (int y = 0; y < n; y++)
             for (int x = 0; x < n; x++) {
-                size_t row = ((size_t)z * n + y) * n, i = row + x, j = row + ((x + 1) % n);
-                float* o = &out[i * 4];
-                o[0] = R(i); o[1] = K(i); o[2] = R(j) - R(i); o[3] = K(j) - K(i);
+                float* o = &out[(((size_t)z * n + y) * n + x) * 16];
+                trilinear_coeffs(fr, n, x, y, z, o);
+                trilinear_coeffs(fk, n, x, y, z, o + 8);
             }
 }
 void pack_small_f(const std::vector<uint8_t>& rgba, int n, std::vector<float>& out) {
-    out.resize((size_t)n * n * n * 4);
-    auto Hh = [&](int x, int y, int z) {
-        size_t i = (((size_t)z * n + (y % n)) * n + (x % n));
-        return un8(rgba[i * 4]) * 0.625f + un8(rgba[i * 4 + 1]) * 0.25f + un8(rgba[i * 4 + 2]) * 0.125f;
-    };
+    std::vector<float> Hh((size_t)n * n * n);
+    for (size_t i = 0; i < Hh.size(); i++) Hh[i] = un8(rgba[i * 4]) * 0.625f + un8(rgba[i * 4 + 1]) * 0.25f + un8(rgba[i * 4 + 2]) * 0.125f;
+    out.resize(Hh.size() * 8);
+    auto fh = [&](int x, int y, int z) { return Hh[((size_t)z * n + y) * n + x]; };
     for (int z = 0; z < n; z++)
         for (int y = 0; y < n; y++)
-            for (int x = 0; x < n; x++) {
-                float* o = &out[((((size_t)z * n + y) * n) + x) * 4];
-                float h00 = Hh(x, y, z), h10 = Hh(x + 1, y, z), h01 = Hh(x, y + 1, z), h11 = Hh(x + 1, y + 1, z);
-                o[0] = h00; o[1] = h10 - h00; o[2] = h01 - h00; o[3] = (h11 - h01) - (h10 - h00);
-            }
+            for (int x = 0; x < n; x++) trilinear_coeffs(fh, n, x, y, z, &out[(((size_t)z * n + y) * n + x) * 8]);
 }
 void pack_weather_f(const std::vector<uint8_t>& rgba, int w, int h, std::vector<float>& out) {
-    out.resize((size_t)w * h * 4);
+    out.resize((size_t)w * h * 8);
     for (int y = 0; y < h; y++)
         for (int x = 0; x < w; x++) {
-            size_t i = (size_t)y * w + x, j = (size_t)y * w + ((x + 1) % w);
-            float* o = &out[i * 4];
-            o[0] = un8(rgba[i * 4]); o[1] = un8(rgba[i * 4 + 2]); o[2] = un8(rgba[j * 4]) - o[0]; o[3] = un8(rgba[j * 4 + 2]) - o[1];
+            int x1 = (x + 1) % w, y1 = (y + 1) % h;
+            float* o = &out[((size_t)y * w + x) * 8];
+            for (int ch = 0; ch < 2; ch++) {  // ch 0: cloud type (R), ch 1: coverage (B)
+                int k = ch == 0 ? 0 : 2;
+                float v00 = un8(rgba[((size_t)y * w + x) * 4 + k]), v10 = un8(rgba[((size_t)y * w + x1) * 4 + k]);
+                float v01 = un8(rgba[((size_t)y1 * w + x) * 4 + k]), v11 = un8(rgba[((size_t)y1 * w + x1) * 4 + k]);
+                o[ch * 4 + 0] = v00; o[ch * 4 + 1] = v10 - v00; o[ch * 4 + 2] = v01 - v00; o[ch * 4 + 3] = (v11 - v01) - (v10 - v00);
+            }
         }
 }
 int ilog2(int v) { int s = 0; while ((1 << s) < v) s++; return s; }
@@ -149,6 +174,8 @@ int upload_levels(cs_context* c, const std::vector<uint8_t>& large0, int ln, con
     c->large_n = ln; c->large_levels = (int)c->h_large.size();
     c->small_n = sn; c->small_levels = (int)c->h_small.size();
     c->weather_w = ww; c->weather_h = wh;
+    c->weather_type_hi = 1;
+    for (size_t i = 0; i < weather.size(); i += 4) if (weather[i] < 128) { c->weather_type_hi = 0; break; }
     std::vector<float> pk;
     for (int l = 0; l < c->large_levels; l++) {
         CU(cudaMalloc(&c->d_large[l], c->h_large[l].size()));
@@ -194,6 +221,7 @@ int make_launch(cs_context* c, const cs_cloud_params* P, int x0, int y0, int x1,
     L.weather = c->d_weather; L.weather_f = c->d_weather_f;
     L.large_shift = ilog2(c->large_n); L.small_shift = ilog2(c->small_n);
     L.weather_shx = ilog2(c->weather_w); L.weather_shy = ilog2(c->weather_h);
+    L.weather_type_hi = c->weather_type_hi;
     L.sky_lut = c->d_sky;
     L.frame_consts = c->d_frame_consts;
     L.out = out;

@@ -42,11 +42,12 @@ struct CloudLaunch {
     const uint32_t* large[kMaxLargeLevels];   // RGBA8 texels, x fastest
     const uint32_t* small[kMaxSmallLevels];   // RGBA8 texels (alpha unused)
     const uint32_t* weather;                  // RGBA8 texels
-    // fp32 neighbour-pair layouts for the fast kernel (see clouds_fast.cu)
+    // fp32 interpolation-coefficient records for the fast kernel (see context.cu / clouds_fast.cu)
     int large_shift, small_shift, weather_shx, weather_shy;  // log2 of the level-0 edges
-    const float* large_f[kMaxLargeLevels];  // float4 {R, fbm, dR, dfbm} (delta to texel x+1) per texel
-    const float* small_f[kMaxSmallLevels];  // float4 {h, dx, dy, dxy} bilinear deltas per texel
-    const float* weather_f;                 // float4 {type, coverage, dtype, dcoverage} per texel
+    int weather_type_hi;  // 1 when every weather texel has R >= 128 (cloud type >= 0.5): affine height-gradient fast path
+    const float* large_f[kMaxLargeLevels];  // 64 B per texel: 8 trilinear coefficients of R, then 8 of fbm
+    const float* small_f[kMaxSmallLevels];  // 32 B per texel: 8 trilinear coefficients of hfbm
+    const float* weather_f;                 // 32 B per texel: 4 bilinear coefficients of type, then 4 of coverage
     const uint16_t* sky_lut;                    // half4 200x100
     const float* frame_consts;                  // FrameConsts written by the prologue kernel
     uint16_t* out;                              // half4 image

@@ -82,6 +82,38 @@ def test_clouds_match_oracle(cs, pair, helpers, oracle_lib, product_lib, case, m
     assert mx < 0.1
 
 
+def test_all_cloud_types_and_small_volumes(cs, helpers, oracle_lib, product_lib):
+    """Weather map whose cloud type spans 0..1 (stratus / stratocumulus / cumulus mixes: the general
+    mixGradients path, clouds.glsl:82-90) on small non-reference volume sizes (16^3 / 8^3 / 32^2)."""
+    from cloudsky_b200 import assets
+    large, small, weather = assets.synthetic_textures(seed=11, large_n=16, small_n=8, weather_n=32)
+    rng = np.random.default_rng(5)
+    weather = weather.copy()
+    weather[..., 0] = rng.integers(0, 256, weather.shape[:2], dtype=np.uint8)   # type on both sides of 0.5
+    weather[..., 2] = rng.integers(60, 256, weather.shape[:2], dtype=np.uint8)
+    W, H = 128, 64
+    o = helpers.prepared_context(oracle_lib, (large, small, weather), W, H, threads=helpers.cpu_threads)
+    g = helpers.prepared_context(product_lib, (large, small, weather), W, H)
+    for lvl in range(5):  # the library's mip chain is the oracle's, bit for bit
+        assert (g.read_volume_level(0, 16, lvl) == o.read_volume_level(0, 16, lvl)).all()
+    for lvl in range(4):
+        assert (g.read_volume_level(1, 8, lvl) == o.read_volume_level(1, 8, lvl)).all()
+    g.write_sky_lut(o.read_sky_lut())
+    for kw in (dict(coverage=0.6), dict(coverage=1.0, time=5.0, wind_direction=2.0), dict(coverage=0.0)):
+        p = helpers.make_params(product_lib, W, H, **kw)
+        o.render_frame(p)
+        ref = o.read_image()
+        for mode, atol, rtol, need in ((cs.MODE_STRICT, 1e-3, 2e-3, 0.999), (cs.MODE_FAST, 2e-3, 1e-2, 0.998)):
+            g.set_march_config(128, 6, mode)
+            g.render_frame(p)
+            out = g.read_image()
+            assert np.isfinite(out.astype(np.float32)).all()
+            frac, mx = helpers.compare_images(out, ref, atol, rtol)
+            assert frac >= need, (kw, mode, frac, mx)
+    assert (ref == 0).all()  # coverage 0 -> empty image (remap by zero must not leak NaN, clouds.glsl:124)
+    o.close(); g.close()
+
+
 def test_counters_match_oracle(cs, pair, helpers, oracle_lib, product_lib):
     o, g, W, H = pair
     p = helpers.make_params(product_lib, W, H)
