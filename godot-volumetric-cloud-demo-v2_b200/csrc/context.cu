@@ -3,9 +3,10 @@
 //
 // HBM layout per context (everything stays resident; the part of it a frame touches, ~40 MiB, lives in
 // L2 after the first frame):
-//   large volume : RGBA8 mip chain 128^3 .. 1^3 (9.14 MiB, strict kernel) + 64-B coefficient records (146 MiB, fast kernel)
-//   small volume : RGBA8 mip chain 32^3 .. 1^3 (146 KiB)                  + 32-B coefficient records (1.14 MiB)
-//   weather map  : RGBA8 512^2 (1 MiB)                                    + 32-B coefficient records (8 MiB)
+//   large volume : RGBA8 mip chain 128^3 .. 1^3 (9.14 MiB, strict kernel) + coefficient records (fast kernel): fp16 32 B/texel
+//                  = 73 MiB when exactly representable, else fp32 64 B/texel = 146 MiB
+//   small volume : RGBA8 mip chain 32^3 .. 1^3 (146 KiB)                  + records 16 / 32 B per texel (0.57 / 1.14 MiB)
+//   weather map  : RGBA8 512^2 (1 MiB)                                    + records 16 / 32 B per texel (4 / 8 MiB)
 //   transmittance LUT 256x64 half4, sky LUT 200x100 half4, FrameConsts (64 B)
 //   output image : W*H half4, tightly packed, row 0 = uv.y 0
 #include <cuda_runtime.h>
@@ -30,6 +31,7 @@ struct cs_context {
     bool have_tex = false;
     int large_n = 0, large_levels = 0, small_n = 0, small_levels = 0, weather_w = 0, weather_h = 0;
     int weather_type_hi = 0;
+    int records_half = 0;  // 1: d_*_f hold exact-integer fp16 records, 0: fp32 records
     uint32_t* d_large[kMaxLargeLevels] = {};
     uint32_t* d_small[kMaxSmallLevels] = {};
     uint32_t* d_weather = nullptr;
@@ -49,7 +51,7 @@ struct cs_context {
     uint16_t* d_image = nullptr;
 
     // march config
-    int primary_steps = CS_REF_PRIMARY_STEPS, cone_samples = CS_REF_CONE_SAMPLES, mode = CS_MODE_FAST;
+    int primary_steps = CS_REF_PRIMARY_STEPS, cone_samples = CS_REF_CONE_SAMPLES, mode = CS_MODE_FAST, variant = 0;
     bool counters_on = false;
     unsigned long long* d_counters = nullptr;
 
@@ -156,10 +158,85 @@ void pack_weather_f(const std::vector<uint8_t>& rgba, int w, int h, std::vector<
             }
         }
 }
+// ---- compact records: the same coefficients as exact INTEGERS in fp16 ---------------------------------------
+// All inputs are 8-bit texels, so R, K = 5G+2B+A, h = 5R+2G+B and the weather channels are integers and so are
+// all their interpolation coefficients (differences of differences).  fp16 holds every integer of magnitude
+// <= 2048 exactly (and even / multiple-of-4 ones beyond), which covers smooth noise textures such as the
+// reference's.  When EVERY coefficient of EVERY level is exactly representable the fast kernel reads these
+// half-size records (large 32 B, small 16 B, weather 16 B: half the L1 wavefronts per fetch) and scales the
+// interpolated integer by 1/255 or 1/2040 afterwards; otherwise it falls back to the fp32 records above.
+inline bool half_exact(int v) {
+    int a = v < 0 ? -v : v;
+    if (a <= 2048) return true;
+    if (a <= 4096) return (a & 1) == 0;
+    if (a <= 8192) return (a & 3) == 0;
+    if (a <= 16384) return (a & 7) == 0;
+    return false;
+}
+inline uint16_t half_bits_exact(int v) {  // v must satisfy half_exact()
+    if (v == 0) return 0;
+    uint16_t sign = v < 0 ? 0x8000u : 0u;
+    unsigned a = (unsigned)(v < 0 ? -v : v);
+    int e = 31 - __builtin_clz(a);
+    unsigned mant = e <= 10 ? (a << (10 - e)) : (a >> (e - 10));
+    return (uint16_t)(sign | ((unsigned)(e + 15) << 10) | (mant & 0x3ffu));
+}
+template <class F>
+bool trilinear_coeffs_i(F v, int n, int x, int y, int z, uint16_t* c) {
+    int x1 = (x + 1) % n, y1 = (y + 1) % n, z1 = (z + 1) % n;
+    int v000 = v(x, y, z), v100 = v(x1, y, z), v010 = v(x, y1, z), v110 = v(x1, y1, z);
+    int v001 = v(x, y, z1), v101 = v(x1, y, z1), v011 = v(x, y1, z1), v111 = v(x1, y1, z1);
+    int k[8];
+    k[0] = v000; k[1] = v100 - v000; k[2] = v010 - v000; k[3] = (v110 - v010) - k[1];
+    k[4] = v001 - v000; k[5] = (v101 - v001) - k[1]; k[6] = (v011 - v001) - k[2];
+    k[7] = ((v111 - v011) - (v101 - v001)) - k[3];
+    bool ok = true;
+    for (int i = 0; i < 8; i++) { ok = ok && half_exact(k[i]); c[i] = ok ? half_bits_exact(k[i]) : 0; }
+    return ok;
+}
+bool pack_large_h(const std::vector<uint8_t>& rgba, int n, std::vector<uint16_t>& out) {
+    out.resize((size_t)n * n * n * 16);
+    auto fr = [&](int x, int y, int z) { return (int)rgba[(((size_t)z * n + y) * n + x) * 4]; };
+    auto fk = [&](int x, int y, int z) { const uint8_t* t = &rgba[(((size_t)z * n + y) * n + x) * 4]; return 5 * t[1] + 2 * t[2] + t[3]; };
+    for (int z = 0; z < n; z++)
+        for (int y = 0; y < n; y++)
+            for (int x = 0; x < n; x++) {
+                uint16_t* o = &out[(((size_t)z * n + y) * n + x) * 16];
+                if (!trilinear_coeffs_i(fr, n, x, y, z, o) || !trilinear_coeffs_i(fk, n, x, y, z, o + 8)) return false;
+            }
+    return true;
+}
+bool pack_small_h(const std::vector<uint8_t>& rgba, int n, std::vector<uint16_t>& out) {
+    out.resize((size_t)n * n * n * 8);
+    auto fh = [&](int x, int y, int z) { const uint8_t* t = &rgba[(((size_t)z * n + y) * n + x) * 4]; return 5 * t[0] + 2 * t[1] + t[2]; };
+    for (int z = 0; z < n; z++)
+        for (int y = 0; y < n; y++)
+            for (int x = 0; x < n; x++)
+                if (!trilinear_coeffs_i(fh, n, x, y, z, &out[(((size_t)z * n + y) * n + x) * 8])) return false;
+    return true;
+}
+bool pack_weather_h(const std::vector<uint8_t>& rgba, int w, int h, std::vector<uint16_t>& out) {
+    out.resize((size_t)w * h * 8);
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            int x1 = (x + 1) % w, y1 = (y + 1) % h;
+            uint16_t* o = &out[((size_t)y * w + x) * 8];
+            for (int ch = 0; ch < 2; ch++) {
+                int k = ch == 0 ? 0 : 2;
+                int v00 = rgba[((size_t)y * w + x) * 4 + k], v10 = rgba[((size_t)y * w + x1) * 4 + k];
+                int v01 = rgba[((size_t)y1 * w + x) * 4 + k], v11 = rgba[((size_t)y1 * w + x1) * 4 + k];
+                int c[4] = {v00, v10 - v00, v01 - v00, (v11 - v01) - (v10 - v00)};  // |c| <= 510: always exact in fp16
+                for (int i = 0; i < 4; i++) o[ch * 4 + i] = half_bits_exact(c[i]);
+            }
+        }
+    return true;
+}
+
 int ilog2(int v) { int s = 0; while ((1 << s) < v) s++; return s; }
 
 int upload_levels(cs_context* c, const std::vector<uint8_t>& large0, int ln, const std::vector<uint8_t>& small0, int sn,
                   const std::vector<uint8_t>& weather, int ww, int wh) {
+    const bool force_fp32_records = getenv("CLOUDSKY_FP32_RECORDS") != nullptr;  // development / test knob
     if (!is_pow2(ln) || !is_pow2(sn) || !is_pow2(ww) || !is_pow2(wh))
         return fail(c, CS_ERR_INVALID, "texture dimensions must be powers of two (REPEAT addressing uses masks)");
     if (ln > 128 || sn > 32) return fail(c, CS_ERR_INVALID, "volume too large (large <= 128^3, small <= 32^3)");
@@ -176,26 +253,40 @@ int upload_levels(cs_context* c, const std::vector<uint8_t>& large0, int ln, con
     c->weather_w = ww; c->weather_h = wh;
     c->weather_type_hi = 1;
     for (size_t i = 0; i < weather.size(); i += 4) if (weather[i] < 128) { c->weather_type_hi = 0; break; }
-    std::vector<float> pk;
     for (int l = 0; l < c->large_levels; l++) {
         CU(cudaMalloc(&c->d_large[l], c->h_large[l].size()));
         CU(cudaMemcpy(c->d_large[l], c->h_large[l].data(), c->h_large[l].size(), cudaMemcpyHostToDevice));
-        pack_large_f(c->h_large[l], ln >> l, pk);
-        CU(cudaMalloc(&c->d_large_f[l], pk.size() * 4));
-        CU(cudaMemcpy(c->d_large_f[l], pk.data(), pk.size() * 4, cudaMemcpyHostToDevice));
     }
     for (int l = 0; l < c->small_levels; l++) {
         CU(cudaMalloc(&c->d_small[l], c->h_small[l].size()));
         CU(cudaMemcpy(c->d_small[l], c->h_small[l].data(), c->h_small[l].size(), cudaMemcpyHostToDevice));
-        pack_small_f(c->h_small[l], sn >> l, pk);
-        CU(cudaMalloc(&c->d_small_f[l], pk.size() * 4));
-        CU(cudaMemcpy(c->d_small_f[l], pk.data(), pk.size() * 4, cudaMemcpyHostToDevice));
     }
     CU(cudaMalloc(&c->d_weather, weather.size()));
     CU(cudaMemcpy(c->d_weather, weather.data(), weather.size(), cudaMemcpyHostToDevice));
-    pack_weather_f(weather, ww, wh, pk);
-    CU(cudaMalloc(&c->d_weather_f, pk.size() * 4));
-    CU(cudaMemcpy(c->d_weather_f, pk.data(), pk.size() * 4, cudaMemcpyHostToDevice));
+
+    // interpolation records for the fast kernel: exact-integer fp16 records when representable, else fp32
+    std::vector<std::vector<uint16_t>> lh(c->large_levels), sh(c->small_levels);
+    std::vector<uint16_t> wh16;
+    bool half_ok = force_fp32_records ? false : true;
+    for (int l = 0; l < c->large_levels && half_ok; l++) half_ok = pack_large_h(c->h_large[l], ln >> l, lh[l]);
+    for (int l = 0; l < c->small_levels && half_ok; l++) half_ok = pack_small_h(c->h_small[l], sn >> l, sh[l]);
+    if (half_ok) half_ok = pack_weather_h(weather, ww, wh, wh16);
+    c->records_half = half_ok ? 1 : 0;
+    auto put = [&](float** dst, const void* src, size_t bytes) -> cudaError_t {
+        cudaError_t e = cudaMalloc(dst, bytes);
+        return e != cudaSuccess ? e : cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
+    };
+    std::vector<float> pk;
+    for (int l = 0; l < c->large_levels; l++) {
+        if (half_ok) { CU(put(&c->d_large_f[l], lh[l].data(), lh[l].size() * 2)); }
+        else { pack_large_f(c->h_large[l], ln >> l, pk); CU(put(&c->d_large_f[l], pk.data(), pk.size() * 4)); }
+    }
+    for (int l = 0; l < c->small_levels; l++) {
+        if (half_ok) { CU(put(&c->d_small_f[l], sh[l].data(), sh[l].size() * 2)); }
+        else { pack_small_f(c->h_small[l], sn >> l, pk); CU(put(&c->d_small_f[l], pk.data(), pk.size() * 4)); }
+    }
+    if (half_ok) { CU(put(&c->d_weather_f, wh16.data(), wh16.size() * 2)); }
+    else { pack_weather_f(weather, ww, wh, pk); CU(put(&c->d_weather_f, pk.data(), pk.size() * 4)); }
     c->have_tex = true;
     return CS_OK;
 }
@@ -222,6 +313,12 @@ int make_launch(cs_context* c, const cs_cloud_params* P, int x0, int y0, int x1,
     L.large_shift = ilog2(c->large_n); L.small_shift = ilog2(c->small_n);
     L.weather_shx = ilog2(c->weather_w); L.weather_shy = ilog2(c->weather_h);
     L.weather_type_hi = c->weather_type_hi;
+    L.variant = c->variant;
+    L.records_half = c->records_half;
+    // texels per metre at level 0 (exact: power-of-two edge times the shader's texture scale, clouds.glsl:117,132)
+    L.large_fn0 = (float)c->large_n * 0.00008f; L.small_fn0 = (float)c->small_n * 0.001f;
+    L.weather_fw = (float)c->weather_w; L.weather_fh = (float)c->weather_h;
+    L.large_mask0 = c->large_n - 1; L.small_mask0 = c->small_n - 1; L.weather_maskx = c->weather_w - 1; L.weather_masky = c->weather_h - 1;
     L.sky_lut = c->d_sky;
     L.frame_consts = c->d_frame_consts;
     L.out = out;
@@ -457,9 +554,11 @@ int cs_resize(cs_context* c, int w, int h) {
 }
 int cs_set_march_config(cs_context* c, int p, int cone, int mode) {
     if (!c) return CS_ERR_INVALID;
+    int variant = (mode >> 8) & 0xff;  // development knob: fast-kernel variant, 0 = production
+    mode &= 0xff;
     if (p < 1 || p > 4096 || cone < 0 || cone > 64 || (mode != CS_MODE_FAST && mode != CS_MODE_STRICT))
         return fail(c, CS_ERR_INVALID, "cs_set_march_config: primary_steps in [1,4096], cone_samples in [0,64], mode FAST|STRICT");
-    c->primary_steps = p; c->cone_samples = cone; c->mode = mode;
+    c->primary_steps = p; c->cone_samples = cone; c->mode = mode; c->variant = variant;
     return CS_OK;
 }
 int cs_set_counters_enabled(cs_context* c, int on) {

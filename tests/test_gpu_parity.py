@@ -3,9 +3,10 @@
 Tolerances (stated here, justified in DESIGN.md §Parity):
   * LUTs (accurate kernels, --fmad=false):   |gpu - oracle| <= 1e-3 + 2e-3*|oracle|  on every texel
   * clouds STRICT (oracle operation order):  <= 1e-3 + 2e-3*|oracle| on >= 99.9 % of pixels
-  * clouds FAST (FMA + MUFU intrinsics):     <= 2e-3 + 1e-2*|oracle| on >= 99.8 % of pixels
-    (an FMA-contracted build of the oracle itself only reaches 99.91 % at this tolerance —
-     the reference's fp32 arithmetic at 6e6 m is that ill-conditioned near the horizon)
+  * clouds FAST (FMA + MUFU intrinsics):     <= 2e-3 + 1e-2*|oracle| on >= 99.9 % of pixels
+    (SURVEY 8(c)'s recommended criterion; an FMA-contracted build of the oracle itself only reaches
+     99.91 % at this tolerance — the reference's fp32 arithmetic at 6e6 m is that ill-conditioned
+     near the horizon; measured margins are in DESIGN.md section 5)
 """
 import numpy as np
 import pytest
@@ -76,9 +77,11 @@ def test_clouds_match_oracle(cs, pair, helpers, oracle_lib, product_lib, case, m
     if mode == "strict":
         frac, mx = helpers.compare_images(out, ref, 1e-3, 2e-3)
         assert frac >= 0.999, (frac, mx)
+        same = (out[1:, 1:].view(np.uint16) == ref[1:, 1:].view(np.uint16)).all(-1).mean()
+        assert same >= 0.98, same  # the strict kernel is the oracle's arithmetic: measured 99.5-99.9 % bit-identical pixels
     else:
         frac, mx = helpers.compare_images(out, ref, 2e-3, 1e-2)
-        assert frac >= 0.998, (frac, mx)
+        assert frac >= 0.999, (frac, mx)
     assert mx < 0.1
 
 
@@ -103,7 +106,7 @@ def test_all_cloud_types_and_small_volumes(cs, helpers, oracle_lib, product_lib)
         p = helpers.make_params(product_lib, W, H, **kw)
         o.render_frame(p)
         ref = o.read_image()
-        for mode, atol, rtol, need in ((cs.MODE_STRICT, 1e-3, 2e-3, 0.999), (cs.MODE_FAST, 2e-3, 1e-2, 0.998)):
+        for mode, atol, rtol, need in ((cs.MODE_STRICT, 1e-3, 2e-3, 0.999), (cs.MODE_FAST, 2e-3, 1e-2, 0.999)):
             g.set_march_config(128, 6, mode)
             g.render_frame(p)
             out = g.read_image()
@@ -112,6 +115,45 @@ def test_all_cloud_types_and_small_volumes(cs, helpers, oracle_lib, product_lib)
             assert frac >= need, (kw, mode, frac, mx)
     assert (ref == 0).all()  # coverage 0 -> empty image (remap by zero must not leak NaN, clouds.glsl:124)
     o.close(); g.close()
+
+
+def test_record_formats(cs, helpers, oracle_lib, product_lib, textures, monkeypatch):
+    """The fast kernel reads exact-integer fp16 records when every interpolation coefficient is representable
+    (the reference textures are) and fp32 records otherwise; both must match the oracle, and rough random
+    texels (coefficients beyond fp16's exact range) must take the fp32 path automatically."""
+    W, H = 128, 64
+    o = helpers.prepared_context(oracle_lib, textures, W, H, threads=helpers.cpu_threads)
+    p = helpers.make_params(product_lib, W, H, time=4.0)
+    o.render_frame(p)
+    ref = o.read_image()
+    imgs = []
+    for force in (False, True):
+        if force:
+            monkeypatch.setenv("CLOUDSKY_FP32_RECORDS", "1")
+        g = helpers.prepared_context(product_lib, textures, W, H)
+        g.write_sky_lut(o.read_sky_lut())
+        g.set_march_config(128, 6, cs.MODE_FAST)
+        g.render_frame(p)
+        imgs.append(g.read_image())
+        frac, mx = helpers.compare_images(imgs[-1], ref, 2e-3, 1e-2)
+        assert frac >= 0.999, (force, frac, mx)
+        g.close()
+    monkeypatch.delenv("CLOUDSKY_FP32_RECORDS")
+    frac, mx = helpers.compare_images(imgs[0], imgs[1], 1e-3, 2e-3)
+    assert frac >= 0.995, (frac, mx)  # same maths, different rounding of the coefficients
+    # rough random texels: second differences of K = 5G+2B+A exceed 2048 and are odd -> not exact in fp16 -> fp32 records
+    rng = np.random.default_rng(9)
+    large = rng.integers(0, 256, (16, 16, 16, 4), dtype=np.uint8)
+    small = rng.integers(0, 256, (8, 8, 8, 3), dtype=np.uint8)
+    weather = rng.integers(100, 256, (32, 32, 3), dtype=np.uint8)
+    o2 = helpers.prepared_context(oracle_lib, (large, small, weather), W, H, threads=helpers.cpu_threads)
+    g2 = helpers.prepared_context(product_lib, (large, small, weather), W, H)
+    g2.write_sky_lut(o2.read_sky_lut())
+    q = helpers.make_params(product_lib, W, H, coverage=0.7)
+    o2.render_frame(q); g2.set_march_config(128, 6, cs.MODE_FAST); g2.render_frame(q)
+    frac, mx = helpers.compare_images(g2.read_image(), o2.read_image(), 2e-3, 1e-2)
+    assert frac >= 0.998, (frac, mx)
+    o.close(); o2.close(); g2.close()
 
 
 def test_counters_match_oracle(cs, pair, helpers, oracle_lib, product_lib):
@@ -195,7 +237,7 @@ def test_full_size_properties_and_row_subsample(cs, helpers, oracle_lib, product
         d = np.abs(img[r, 1:] - buf[r, 1:].astype(np.float32))
         ok = (d <= 2e-3 + 1e-2 * np.abs(buf[r, 1:].astype(np.float32))).all(-1)
         ok_total += ok.sum(); n_total += ok.size
-    assert ok_total / n_total >= 0.998, ok_total / n_total
+    assert ok_total / n_total >= 0.999, ok_total / n_total
     # tile/row-band invariance at full size: two half-frames into caller-owned device memory
     import ctypes
     g.render_rows_to(p, 0, H // 2, g.image_device_ptr())
