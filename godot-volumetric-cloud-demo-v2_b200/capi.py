@@ -140,6 +140,8 @@ _PROTOTYPES = {
     "cs_image_device_ptr": (_P, [_P]),
     "cs_read_image": (C.c_int, [_P, _P, C.c_size_t]),
     "cs_render_frame_host": (C.c_int, [_P, C.POINTER(CloudParams), _P, C.c_size_t]),
+    "cs_render_frame_host_async": (C.c_int, [_P, C.POINTER(CloudParams), _P, C.c_size_t]),
+    "cs_wait_host": (C.c_int, [_P]),
     "cs_render_sun_batch_to": (C.c_int, [_P, C.POINTER(CloudParams), C.POINTER(C.c_float), C.c_int, _P]),
     "cs_time_render_frame": (C.c_int, [_P, C.POINTER(CloudParams), C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "cs_set_kernel_timing": (C.c_int, [_P, C.c_int]),
@@ -368,6 +370,13 @@ class Context:
         assert out.nbytes == nbytes and out.flags.c_contiguous
         self._ck(self.lib.dll.cs_render_frame_host(self._h, C.byref(params), out.ctypes.data, nbytes))
         return out
+
+    def render_frame_host_async(self, params: CloudParams, out_ptr: int) -> None:
+        """Queue sky LUT + march + D2H into host memory at out_ptr (valid after wait_host())."""
+        self._ck(self.lib.dll.cs_render_frame_host_async(self._h, C.byref(params), _P(out_ptr), self.width * self.height * 8))
+
+    def wait_host(self) -> None:
+        self._ck(self.lib.dll.cs_wait_host(self._h))
 
     def render_sun_batch_to(self, params: CloudParams, sun_dirs: np.ndarray, device_ptr: int) -> None:
         s = np.ascontiguousarray(sun_dirs, dtype=np.float32).reshape(-1, 3)

@@ -49,6 +49,12 @@ struct cs_context {
     // output
     int W = 0, H = 0;
     uint16_t* d_image = nullptr;
+    // streaming host readback (cs_render_frame_host_async): second image, copy stream, per-slot events
+    uint16_t* d_image2 = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_rendered[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+    bool slot_busy[2] = {false, false};
+    unsigned async_frame = 0;
 
     // march config
     int primary_steps = CS_REF_PRIMARY_STEPS, cone_samples = CS_REF_CONE_SAMPLES, mode = CS_MODE_FAST, variant = 0;
@@ -545,7 +551,10 @@ int cs_resize(cs_context* c, int w, int h) {
     int r = bind(c);
     if (r) return r;
     CU(cudaStreamSynchronize(c->stream));
+    if (c->copy_stream) CU(cudaStreamSynchronize(c->copy_stream));
     if (c->d_image) { cudaFree(c->d_image); c->d_image = nullptr; }
+    if (c->d_image2) { cudaFree(c->d_image2); c->d_image2 = nullptr; }
+    c->slot_busy[0] = c->slot_busy[1] = false;
     c->W = c->H = 0;
     CU(cudaMalloc(&c->d_image, (size_t)w * h * 8));
     CU(cudaMemsetAsync(c->d_image, 0, (size_t)w * h * 8, c->stream));
@@ -628,6 +637,42 @@ int cs_render_frame_host(cs_context* c, const cs_cloud_params* P, uint16_t* out,
     if (r) return r;
     CU(cudaMemcpyAsync(out, c->d_image, bytes, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    return CS_OK;
+}
+int cs_render_frame_host_async(cs_context* c, const cs_cloud_params* P, uint16_t* out, size_t bytes) {
+    if (!c || !P || !out) return CS_ERR_INVALID;
+    if (bytes != (size_t)c->W * c->H * 8) return fail(c, CS_ERR_INVALID, "cs_render_frame_host_async: bad buffer size");
+    int r = bind(c);
+    if (r) return r;
+    if (!c->copy_stream) {
+        CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            CU(cudaEventCreateWithFlags(&c->ev_rendered[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
+        }
+    }
+    if (!c->d_image2) CU(cudaMalloc(&c->d_image2, bytes));
+    const int slot = (int)(c->async_frame++ & 1u);
+    uint16_t* img = slot ? c->d_image2 : c->d_image;
+    if (c->slot_busy[slot]) CU(cudaStreamWaitEvent(c->stream, c->ev_copied[slot], 0));  // the image is free once its last copy finished
+    r = cs_build_sky_lut(c, P->light_direction);
+    if (r) return r;
+    r = dispatch(c, P, 0, 0, c->W, c->H, img);
+    if (r) return r;
+    CU(cudaEventRecord(c->ev_rendered[slot], c->stream));
+    CU(cudaStreamWaitEvent(c->copy_stream, c->ev_rendered[slot], 0));
+    CU(cudaMemcpyAsync(out, img, bytes, cudaMemcpyDeviceToHost, c->copy_stream));
+    CU(cudaEventRecord(c->ev_copied[slot], c->copy_stream));
+    c->slot_busy[slot] = true;
+    return CS_OK;
+}
+int cs_wait_host(cs_context* c) {
+    if (!c) return CS_ERR_INVALID;
+    int r = bind(c);
+    if (r) return r;
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->copy_stream) CU(cudaStreamSynchronize(c->copy_stream));
+    c->slot_busy[0] = c->slot_busy[1] = false;
     return CS_OK;
 }
 int cs_render_sun_batch_to(cs_context* c, const cs_cloud_params* P, const float* suns, int n, void* out) {

@@ -205,6 +205,13 @@ int cs_read_image(cs_context* ctx, uint16_t* out_half4, size_t out_bytes);
  * This is the _update_per_frame_data + _render_process pair (cloud_sky.gd:165-187,234-248). */
 int cs_render_frame_host(cs_context* ctx, const cs_cloud_params* params, uint16_t* out_half4,
                          size_t out_bytes);
+/* Streaming variant of cs_render_frame_host for back-to-back frames: the kernels of frame k+1 overlap the
+ * device->host copy of frame k (two device images, a copy stream, events).  The call returns as soon as the work
+ * is queued; out_half4 (pinned memory recommended) is valid after cs_wait_host(ctx).  At most two frames are in
+ * flight; a third call waits for the oldest copy.  This is update_sky's steady state (cloud_sky.gd:129-163) for
+ * a caller that consumes the texture on the host. */
+int cs_render_frame_host_async(cs_context* ctx, const cs_cloud_params* params, uint16_t* out_half4, size_t out_bytes);
+int cs_wait_host(cs_context* ctx);
 /* Sun-angle batch (BASELINE config 4): for each of n suns build its sky LUT and render one full
  * frame into device_out_half4 + i*W*H*4 halfs.  Other params are shared. */
 int cs_render_sun_batch_to(cs_context* ctx, const cs_cloud_params* params, const float* sun_dirs_xyz,

@@ -776,6 +776,8 @@ int cs_render_frame_host(cs_context* c, const cs_cloud_params* P, uint16_t* out,
     r = cs_render_frame(c, P); if (r) return r;
     memcpy(out, c->image.data(), bytes); return CS_OK;
 }
+int cs_render_frame_host_async(cs_context* c, const cs_cloud_params* P, uint16_t* out, size_t bytes) { return cs_render_frame_host(c, P, out, bytes); }
+int cs_wait_host(cs_context*) { return CS_OK; }
 int cs_render_sun_batch_to(cs_context* c, const cs_cloud_params* P, const float* suns, int n, void* out) {
     if (!c || !P || !suns || !out || n < 1) return CS_ERR_INVALID;
     for (int i = 0; i < n; i++) {
