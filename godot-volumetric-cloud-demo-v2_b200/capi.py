@@ -109,6 +109,46 @@ class Counters(C.Structure):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}
 
 
+class View(C.Structure):
+    """cs_view: which directions the presentation composite shades (clouds.gdshader EYEDIR)."""
+    _fields_ = [
+        ("projection", C.c_int32), ("width", C.c_int32), ("height", C.c_int32),
+        ("basis_columns", C.c_float * 9), ("fov_y_degrees", C.c_float),
+        ("sun_direction", C.c_float * 3), ("sun_disk_scale", C.c_float), ("blend_amount", C.c_float),
+    ]
+
+    @classmethod
+    def equirect(cls, width, height, sun_direction, sun_disk_scale=1.0, blend_amount=0.0):
+        v = cls()
+        v.projection, v.width, v.height = 0, width, height
+        v.basis_columns[:] = [1, 0, 0, 0, 1, 0, 0, 0, 1]
+        v.fov_y_degrees = 75.0
+        v.sun_direction[:] = [float(x) for x in sun_direction]
+        v.sun_disk_scale, v.blend_amount = sun_disk_scale, blend_amount
+        return v
+
+    @classmethod
+    def perspective(cls, width, height, basis_columns, fov_y_degrees, sun_direction, sun_disk_scale=1.0, blend_amount=0.0):
+        v = cls.equirect(width, height, sun_direction, sun_disk_scale, blend_amount)
+        v.projection = 1
+        v.basis_columns[:] = [float(x) for x in basis_columns]
+        v.fov_y_degrees = fov_y_degrees
+        return v
+
+
+class SkyFrame(C.Structure):
+    """cs_sky_frame: the observable state of the Sky resource (cloud_sky.gd:82-94, sky_lut.gd:15-18)."""
+    _fields_ = [
+        ("frame", C.c_int32), ("frames_to_update", C.c_int32), ("texture_size", C.c_int32),
+        ("update_position", C.c_int32 * 2), ("update_region_size", C.c_int32), ("num_workgroups", C.c_int32),
+        ("texture_to_update", C.c_int32), ("texture_to_blend_from", C.c_int32), ("texture_to_blend_to", C.c_int32),
+        ("blend_amount", C.c_float),
+        ("sky_current_texture", C.c_int32), ("sky_blend_from", C.c_int32), ("sky_blend_to", C.c_int32), ("sky_updates", C.c_int32),
+        ("cloud_textures", C.c_void_p * 3), ("sky_luts", C.c_void_p * 3),
+        ("frame_data", FrameState),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/cloudsky.h declares.
 _P = C.c_void_p
 _PROTOTYPES = {
@@ -144,6 +184,15 @@ _PROTOTYPES = {
     "cs_wait_host": (C.c_int, [_P]),
     "cs_render_sun_batch_to": (C.c_int, [_P, C.POINTER(CloudParams), C.POINTER(C.c_float), C.c_int, _P]),
     "cs_time_render_frame": (C.c_int, [_P, C.POINTER(CloudParams), C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    "cs_sky_create": (C.c_int, [_P, C.POINTER(SkySettings), C.POINTER(_P)]),
+    "cs_sky_destroy": (None, [_P]),
+    "cs_sky_set_settings": (C.c_int, [_P, C.POINTER(SkySettings)]),
+    "cs_sky_set_sun": (C.c_int, [_P, C.POINTER(C.c_float), C.c_float, C.POINTER(C.c_float)]),
+    "cs_sky_update": (C.c_int, [_P, C.c_float]),
+    "cs_sky_get_frame": (C.c_int, [_P, C.POINTER(SkyFrame)]),
+    "cs_sky_read_texture": (C.c_int, [_P, C.c_int, _P, C.c_size_t]),
+    "cs_composite": (C.c_int, [_P, C.POINTER(View), _P, _P, C.c_int, C.c_int, _P, _P, _P]),
+    "cs_sky_composite_host": (C.c_int, [_P, C.POINTER(View), _P, C.c_size_t]),
     "cs_set_kernel_timing": (C.c_int, [_P, C.c_int]),
     "cs_read_kernel_timings": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "cs_settings_default": (None, [C.POINTER(SkySettings)]),
@@ -395,6 +444,48 @@ class Context:
         ms = C.c_float()
         self._ck(self.lib.dll.cs_time_render_frame(self._h, C.byref(params), warmup, iters, C.byref(ms)))
         return float(ms.value)
+
+
+class Sky:
+    """cs_sky: the time-sliced Sky resource (cloud_sky.gd's update_sky state machine inside the library)."""
+
+    def __init__(self, ctx: Context, settings: SkySettings):
+        self.ctx = ctx
+        self._h = _P()
+        ctx._ck(ctx.lib.dll.cs_sky_create(ctx._h, C.byref(settings), C.byref(self._h)))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self.ctx.lib.dll.cs_sky_destroy(self._h)
+            self._h = None
+
+    def set_settings(self, settings: SkySettings) -> None:
+        self.ctx._ck(self.ctx.lib.dll.cs_sky_set_settings(self._h, C.byref(settings)))
+
+    def set_sun(self, basis_columns, energy: float, color_srgb) -> None:
+        b = (C.c_float * 9)(*[float(v) for v in basis_columns])
+        c = (C.c_float * 3)(*[float(v) for v in color_srgb])
+        self.ctx._ck(self.ctx.lib.dll.cs_sky_set_sun(self._h, b, float(energy), c))
+
+    def update(self, now: float) -> None:
+        self.ctx._ck(self.ctx.lib.dll.cs_sky_update(self._h, float(now)))
+
+    def frame(self) -> SkyFrame:
+        f = SkyFrame()
+        self.ctx._ck(self.ctx.lib.dll.cs_sky_get_frame(self._h, C.byref(f)))
+        return f
+
+    def composite(self, view: "View") -> np.ndarray:
+        """clouds.gdshader for every pixel of `view` with this sky's blend textures; float32 [H, W, 4] linear radiance."""
+        out = np.empty((view.height, view.width, 4), np.float32)
+        self.ctx._ck(self.ctx.lib.dll.cs_sky_composite_host(self._h, C.byref(view), out.ctypes.data, out.nbytes))
+        return out
+
+    def read_texture(self, index: int) -> np.ndarray:
+        n = self.frame().texture_size
+        out = np.empty((n, n, 4), np.float16)
+        self.ctx._ck(self.ctx.lib.dll.cs_sky_read_texture(self._h, index, out.ctypes.data, out.nbytes))
+        return out
 
 
 _product: Optional[Library] = None

@@ -17,55 +17,9 @@
 #include <string>
 #include <vector>
 
-#include "cs_internal.h"
+#include "cs_context.h"
 
 using namespace cs;
-
-struct cs_context {
-    int device = 0;
-    cudaStream_t own_stream = nullptr;
-    cudaStream_t stream = nullptr;
-    std::string err;
-
-    // textures
-    bool have_tex = false;
-    int large_n = 0, large_levels = 0, small_n = 0, small_levels = 0, weather_w = 0, weather_h = 0;
-    int weather_type_hi = 0;
-    int records_half = 0;  // 1: d_*_f hold exact-integer fp16 records, 0: fp32 records
-    uint32_t* d_large[kMaxLargeLevels] = {};
-    uint32_t* d_small[kMaxSmallLevels] = {};
-    uint32_t* d_weather = nullptr;
-    float* d_large_f[kMaxLargeLevels] = {};
-    float* d_small_f[kMaxSmallLevels] = {};
-    float* d_weather_f = nullptr;
-    std::vector<std::vector<uint8_t>> h_large, h_small;  // host copies of the mip chains (readback / repack)
-
-    // LUTs
-    uint16_t* d_tlut = nullptr;
-    uint16_t* d_sky = nullptr;
-    bool have_tlut = false, have_sky = false;
-    float* d_frame_consts = nullptr;
-
-    // output
-    int W = 0, H = 0;
-    uint16_t* d_image = nullptr;
-    // streaming host readback (cs_render_frame_host_async): second image, copy stream, per-slot events
-    uint16_t* d_image2 = nullptr;
-    cudaStream_t copy_stream = nullptr;
-    cudaEvent_t ev_rendered[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
-    bool slot_busy[2] = {false, false};
-    unsigned async_frame = 0;
-
-    // march config
-    int primary_steps = CS_REF_PRIMARY_STEPS, cone_samples = CS_REF_CONE_SAMPLES, mode = CS_MODE_FAST, variant = 0;
-    bool counters_on = false;
-    unsigned long long* d_counters = nullptr;
-
-    // optional per-kernel event timing (cs_set_kernel_timing)
-    bool timing_on = false;
-    std::vector<cudaEvent_t> ev_march, ev_sky;  // begin/end pairs, recycled
-    size_t n_march = 0, n_sky = 0;              // pairs recorded since the last read
-};
 
 namespace {
 
@@ -297,9 +251,9 @@ int upload_levels(cs_context* c, const std::vector<uint8_t>& large0, int ln, con
     return CS_OK;
 }
 
-int make_launch(cs_context* c, const cs_cloud_params* P, int x0, int y0, int x1, int y1, uint16_t* out, CloudLaunch& L) {
+int make_launch(cs_context* c, const cs_cloud_params* P, int x0, int y0, int x1, int y1, uint16_t* out, const uint16_t* sky_lut, CloudLaunch& L) {
     if (!c->have_tex) return fail(c, CS_ERR_NOT_READY, "input textures not uploaded (can_run == false)");
-    if (!c->have_sky) return fail(c, CS_ERR_NOT_READY, "sky LUT not built (Attempting to render with an uninitialized sky lut)");
+    if (!sky_lut && !c->have_sky) return fail(c, CS_ERR_NOT_READY, "sky LUT not built (Attempting to render with an uninitialized sky lut)");
     if (c->W < 1 || !out) return fail(c, CS_ERR_NOT_READY, "cs_resize not called");
     if ((int)P->texture_size[0] != c->W || (int)P->texture_size[1] != c->H)
         return fail(c, CS_ERR_INVALID, "params.texture_size does not match the image size set with cs_resize");
@@ -325,7 +279,7 @@ int make_launch(cs_context* c, const cs_cloud_params* P, int x0, int y0, int x1,
     L.large_fn0 = (float)c->large_n * 0.00008f; L.small_fn0 = (float)c->small_n * 0.001f;
     L.weather_fw = (float)c->weather_w; L.weather_fh = (float)c->weather_h;
     L.large_mask0 = c->large_n - 1; L.small_mask0 = c->small_n - 1; L.weather_maskx = c->weather_w - 1; L.weather_masky = c->weather_h - 1;
-    L.sky_lut = c->d_sky;
+    L.sky_lut = sky_lut ? sky_lut : c->d_sky;
     L.frame_consts = c->d_frame_consts;
     L.out = out;
     L.counters = c->counters_on ? c->d_counters : nullptr;
@@ -343,12 +297,12 @@ void timing_mark(cs_context* c, std::vector<cudaEvent_t>& evs, size_t pair, int 
 }
 
 // prologue + march for one rectangle, asynchronous on c->stream
-int dispatch(cs_context* c, const cs_cloud_params* P, int x0, int y0, int x1, int y1, uint16_t* out) {
+int dispatch(cs_context* c, const cs_cloud_params* P, int x0, int y0, int x1, int y1, uint16_t* out, const uint16_t* sky_lut = nullptr) {
     if (!c || !P) return CS_ERR_INVALID;
     int r = bind(c);
     if (r) return r;
     CloudLaunch L;
-    r = make_launch(c, P, x0, y0, x1, y1, out, L);
+    r = make_launch(c, P, x0, y0, x1, y1, out, sky_lut, L);
     if (r) return r;
     if (L.x1 <= L.x0 || L.y1 <= L.y0) return CS_OK;
     if (L.counters) CU(cudaMemsetAsync(c->d_counters, 0, 6 * sizeof(unsigned long long), c->stream));
@@ -362,6 +316,24 @@ int dispatch(cs_context* c, const cs_cloud_params* P, int x0, int y0, int x1, in
 }
 
 }  // namespace
+
+namespace cs {
+int ctx_dispatch(cs_context* c, const cs_cloud_params* P, int x0, int y0, int x1, int y1, uint16_t* out, const uint16_t* sky_lut) {
+    return dispatch(c, P, x0, y0, x1, y1, out, sky_lut);
+}
+int ctx_build_sky_lut_into(cs_context* c, const float sun[3], uint16_t* dst) {
+    if (!c || !sun || !dst) return CS_ERR_INVALID;
+    if (!c->have_tlut) return fail(c, CS_ERR_NOT_READY, "Attempting to update uninitialized sky lut (build the transmittance LUT first)");
+    int r = bind(c);
+    if (r) return r;
+    if (c->timing_on) timing_mark(c, c->ev_sky, c->n_sky, 0);
+    launch_sky_lut(c->d_tlut, sun, dst, c->stream);
+    if (c->timing_on) timing_mark(c, c->ev_sky, c->n_sky++, 1);
+    CU(cudaGetLastError());
+    return CS_OK;
+}
+int ctx_fail(cs_context* c, int code, const std::string& msg) { return fail(c, code, msg); }
+}  // namespace cs
 
 extern "C" {
 

@@ -1,0 +1,63 @@
+// Internal: the context object shared by context.cu and sky_resource.cu.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "cs_internal.h"
+
+struct cs_context {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string err;
+
+    // textures
+    bool have_tex = false;
+    int large_n = 0, large_levels = 0, small_n = 0, small_levels = 0, weather_w = 0, weather_h = 0;
+    int weather_type_hi = 0;
+    int records_half = 0;  // 1: d_*_f hold exact-integer fp16 records, 0: fp32 records
+    uint32_t* d_large[cs::kMaxLargeLevels] = {};
+    uint32_t* d_small[cs::kMaxSmallLevels] = {};
+    uint32_t* d_weather = nullptr;
+    float* d_large_f[cs::kMaxLargeLevels] = {};
+    float* d_small_f[cs::kMaxSmallLevels] = {};
+    float* d_weather_f = nullptr;
+    std::vector<std::vector<uint8_t>> h_large, h_small;  // host copies of the mip chains (readback / repack)
+
+    // LUTs
+    uint16_t* d_tlut = nullptr;
+    uint16_t* d_sky = nullptr;
+    bool have_tlut = false, have_sky = false;
+    float* d_frame_consts = nullptr;
+
+    // output
+    int W = 0, H = 0;
+    uint16_t* d_image = nullptr;
+    // streaming host readback (cs_render_frame_host_async): second image, copy stream, per-slot events
+    uint16_t* d_image2 = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_rendered[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+    bool slot_busy[2] = {false, false};
+    unsigned async_frame = 0;
+
+    // march config
+    int primary_steps = CS_REF_PRIMARY_STEPS, cone_samples = CS_REF_CONE_SAMPLES, mode = CS_MODE_FAST, variant = 0;
+    bool counters_on = false;
+    unsigned long long* d_counters = nullptr;
+
+    // optional per-kernel event timing (cs_set_kernel_timing)
+    bool timing_on = false;
+    std::vector<cudaEvent_t> ev_march, ev_sky;  // begin/end pairs, recycled
+    size_t n_march = 0, n_sky = 0;              // pairs recorded since the last read
+};
+
+
+namespace cs {
+// prologue + march of one pixel rectangle into `out`, sampling `sky_lut` (nullptr = the context's own LUT).
+int ctx_dispatch(cs_context* c, const cs_cloud_params* P, int x0, int y0, int x1, int y1, uint16_t* out, const uint16_t* sky_lut);
+// sky-LUT kernel into `dst` (device half4[200*100]); requires the transmittance LUT.
+int ctx_build_sky_lut_into(cs_context* c, const float sun[3], uint16_t* dst);
+int ctx_fail(cs_context* c, int code, const std::string& msg);
+}  // namespace cs

@@ -61,6 +61,7 @@ class SkyLUT:
         self.ctx = ctx
         self.light_direction = (0.0, -1.0, 0.0)  # sky_lut.gd:5
         self.needs_update = True
+        self.needs_full_update = True  # sky_lut.gd:10
         self.initialized = transmittance is not None  # sky_lut.gd:7,120
         self.current_texture = 0
         self.updates = 0
@@ -74,6 +75,10 @@ class SkyLUT:
             print("Attempting to update uninitialized sky lut")
             return
         self.render_lut()
+        if self.needs_full_update:  # fill all three copies the first time (sky_lut.gd:49-52)
+            self.render_lut()
+            self.render_lut()
+            self.needs_full_update = False
 
     def render_lut(self) -> None:  # sky_lut.gd:122-148
         self.ctx.build_sky_lut(self.light_direction)

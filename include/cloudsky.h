@@ -221,6 +221,70 @@ int cs_render_sun_batch_to(cs_context* ctx, const cs_cloud_params* params, const
 int cs_time_render_frame(cs_context* ctx, const cs_cloud_params* params, int warmup, int iters,
                          float* out_ms_avg);
 
+/* ---- time-sliced update + temporal blend: the Sky resource of cloud_sky.gd ---------- */
+
+/* One instance of cloud_sky.gd on a context: three hemisphere textures (render target / blend from / blend to,
+ * cloud_sky.gd:213-218), three sky LUTs (sky_lut.gd:15-18), the FrameData accumulators and the tile walk. */
+typedef struct cs_sky cs_sky;
+typedef struct cs_sky_frame {
+    int32_t frame;                 /* tiles rendered so far into the texture being updated (cloud_sky.gd:94)      */
+    int32_t frames_to_update;
+    int32_t texture_size;
+    int32_t update_position[2];    /* origin of the NEXT tile (cloud_sky.gd:82)                                   */
+    int32_t update_region_size, num_workgroups;                       /* cloud_sky.gd:83-84                       */
+    int32_t texture_to_update, texture_to_blend_from, texture_to_blend_to;   /* cloud_sky.gd:87-89                */
+    float blend_amount;            /* frame / frames_to_update as set by the last update (cloud_sky.gd:152)       */
+    int32_t sky_current_texture;   /* sky_lut.gd:18                                                               */
+    int32_t sky_blend_from, sky_blend_to;  /* indices of back_texture[0], back_texture[1] (sky_lut.gd:143-146)    */
+    int32_t sky_updates;           /* number of sky-LUT renders so far                                            */
+    void* cloud_textures[3];       /* device pointers: half4[texture_size * texture_size]                         */
+    void* sky_luts[3];             /* device pointers: half4[200 * 100]                                           */
+    cs_frame_state frame_data;     /* FrameData snapshot used by the texture being updated                        */
+} cs_sky_frame;
+/* load("clouds_sky.tres") + delayed_init (cloud_sky.gd:99-107): allocate the textures for settings->texture_size.
+ * The context must already hold the input textures and the transmittance LUT. */
+int cs_sky_create(cs_context* ctx, const cs_sky_settings* settings, cs_sky** out_sky);
+void cs_sky_destroy(cs_sky* sky);
+/* Property setters (cloud_sky.gd:4-50).  A change of texture_size or frames_to_update runs cleanup() +
+ * update_performance() + request_full_sky_init() like the GDScript setters (cloud_sky.gd:37-50). */
+int cs_sky_set_settings(cs_sky* sky, const cs_sky_settings* settings);
+/* sun.gd:11-13 + FrameData.update_light_data (cloud_sky.gd:76-79): attach / update the sun. */
+int cs_sky_set_sun(cs_sky* sky, const float basis_columns[9], float energy, const float color_srgb[3]);
+/* update_sky() (cloud_sky.gd:129-163) with the clock passed in: renders ONE tile (2 * frames_to_update + 1 tiles
+ * on the first call after a full-init request), rotates the textures when a texture is complete, refreshes the
+ * sky LUT once per texture. */
+int cs_sky_update(cs_sky* sky, float now_seconds);
+int cs_sky_get_frame(cs_sky* sky, cs_sky_frame* out);
+/* Host copy of one of the three hemisphere textures (index 0..2). */
+int cs_sky_read_texture(cs_sky* sky, int index, uint16_t* out_half4, size_t out_bytes);
+
+/* ---- presentation composite: the sky material shader (clouds.gdshader) ------------------- */
+
+/* Which directions to shade.  Equirect: pixel (x, y) looks toward azimuth a = (x+.5)/W*2pi - pi, elevation
+ * e = pi/2 - (y+.5)/H*pi, EYEDIR = (sin a cos e, sin e, -cos a cos e) (Godot axes: +Y up, -Z forward).
+ * Perspective: Godot camera convention, EYEDIR = normalize(basis * (ndc.x * tan(fov/2) * aspect, ndc.y * tan(fov/2), -1)). */
+#define CS_VIEW_EQUIRECT 0
+#define CS_VIEW_PERSPECTIVE 1
+typedef struct cs_view {
+    int32_t projection;      /* CS_VIEW_EQUIRECT or CS_VIEW_PERSPECTIVE                                       */
+    int32_t width, height;   /* output size in pixels                                                       */
+    float basis_columns[9];  /* camera basis (x right, y up, z back), perspective only                      */
+    float fov_y_degrees;     /* perspective only                                                            */
+    float sun_direction[3];  /* LIGHT0_DIRECTION: unit vector toward the sun                                */
+    float sun_disk_scale;    /* uniform sun_disk_scale (clouds.gdshader:13, cloud_sky.gd:27-31)             */
+    float blend_amount;      /* uniform blend_amount (clouds.gdshader:12, cloud_sky.gd:152)                 */
+} cs_view;
+/* sky() of clouds.gdshader:104-116 for every pixel of the view: EYEDIR -> hemi-octahedral lookup of the two cloud
+ * textures (vec3_to_oct, :22-32) blended by blend_amount, get_atmo (:87-102: two sky LUTs / 50, sun disk with bloom
+ * :48-59 attenuated by the transmittance LUT :77-85, hidden below the horizon :62-71), composite and horizon fade
+ * (:114-115).  clouds_from/to: device half4[tex_w*tex_h]; sky_from/to: device half4[200*100]; out: device
+ * float4[width*height] (linear radiance, alpha 1).  Needs the transmittance LUT. */
+int cs_composite(cs_context* ctx, const cs_view* view, const void* clouds_from, const void* clouds_to, int tex_w, int tex_h,
+                 const void* sky_from, const void* sky_to, float* out_rgba32f_device);
+/* The same for a Sky resource's current blend textures / sky-LUT back buffers / blend_amount (view->blend_amount is
+ * ignored), copied to host memory: what the viewport shows for that camera (before tonemapping). */
+int cs_sky_composite_host(cs_sky* sky, const cs_view* view, float* out_rgba32f_host, size_t out_bytes);
+
 /* Per-kernel device timing: when enabled, every sky-LUT build and every cloud-march launch is
  * bracketed by CUDA events on the context's stream.  cs_read_kernel_timings synchronises, returns
  * the summed milliseconds and launch counts since the last read, and resets them. */

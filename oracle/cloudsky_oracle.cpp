@@ -855,6 +855,266 @@ void cs_next_update_position(int* x, int* y, int region, int ts) {  // cloud_sky
 }
 
 
+// ---- the Sky resource: restatement of cloud_sky.gd's update_sky state machine (cloud_sky.gd:109-163) ----------
+}  // extern "C" (reopened below)
+
+struct cs_sky {
+    cs_context* c;
+    cs_sky_settings s;
+    cs_frame_state fd;
+    bool sun_attached = false;
+    float basis[9], energy, color[3];
+    std::vector<uint16_t> textures[3], luts[3];
+    int size = 0, region = 0, groups = 0, pos[2] = {0, 0};
+    int tex_update = 0, tex_from = 1, tex_to = 2, frame = 0;
+    float blend = 0.0f;
+    bool can_run = false, full_init = true, lut_full = true;
+    int lut_current = 0, lut_updates = 0;
+};
+
+static int sky_tick(cs_sky* k, float now);
+
+static void sky_alloc(cs_sky* k) {  // update_performance + texture creation (cloud_sky.gd:109-118,368-402)
+    int ts = k->s.texture_size;
+    cs_update_performance(&ts, k->s.frames_to_update, &k->region, &k->groups);
+    k->s.texture_size = k->size = ts;
+    for (auto& t : k->textures) t.assign((size_t)ts * ts * 4, 0);
+    if (k->c->W != ts || k->c->H != ts) cs_resize(k->c, ts, ts);
+    k->can_run = true;
+}
+static int sky_render_lut(cs_sky* k) {  // sky_lut.gd:122-148
+    int r = cs_build_sky_lut(k->c, k->fd.light_direction);
+    if (r) return r;
+    k->luts[k->lut_current] = k->c->skylut;
+    k->lut_current = (k->lut_current + 1) % 3;
+    k->lut_updates++;
+    return CS_OK;
+}
+static int sky_frame_data(cs_sky* k, float now) {  // cloud_sky.gd:165-187 + sky_lut.gd:43-52
+    if (k->sun_attached) cs_frame_state_set_light(&k->fd, k->basis, k->energy, k->color);
+    cs_frame_advance(&k->fd, &k->s, now);
+    int r = sky_render_lut(k);
+    if (r == CS_OK && k->lut_full) {
+        r = sky_render_lut(k);
+        if (r == CS_OK) r = sky_render_lut(k);
+        k->lut_full = false;
+    }
+    return r;
+}
+static int sky_tick(cs_sky* k, float now) {  // update_sky (cloud_sky.gd:129-163)
+    if (!k->can_run) return CS_OK;
+    int r;
+    if (k->full_init) {
+        k->full_init = false;
+        if ((r = sky_frame_data(k, now)) != CS_OK) return r;                      // initialize_sky (cloud_sky.gd:124-127)
+        for (int i = 0; i < k->s.frames_to_update * 2; i++) if ((r = sky_tick(k, now)) != CS_OK) return r;
+    }
+    if (k->frame >= k->s.frames_to_update) {
+        k->tex_update = (k->tex_update + 1) % 3; k->tex_from = (k->tex_from + 1) % 3; k->tex_to = (k->tex_to + 1) % 3;
+        if ((r = sky_frame_data(k, now)) != CS_OK) return r;
+        k->frame = 0;
+    }
+    k->blend = (float)k->frame / (float)k->s.frames_to_update;
+    cs_cloud_params P;
+    cs_fill_cloud_params(&P, &k->s, &k->fd, k->size, k->size, k->pos[0], k->pos[1]);
+    k->c->skylut = k->luts[(k->lut_current + 2) % 3];  // the LUT rendered last (cloud_sky.gd:242)
+    k->c->have_sky = true;
+    r = render_region(k->c, &P, k->pos[0], k->pos[1], k->pos[0] + 8 * k->groups, k->pos[1] + 8 * k->groups, k->textures[k->tex_update].data());
+    if (r) return r;
+    cs_next_update_position(&k->pos[0], &k->pos[1], k->region, k->size);
+    k->frame++;
+    return CS_OK;
+}
+
+extern "C" {
+
+int cs_sky_create(cs_context* c, const cs_sky_settings* s, cs_sky** out) {
+    if (!c || !s || !out) return CS_ERR_INVALID;
+    *out = nullptr;
+    if (!c->have_tex || !c->have_tlut) return fail(c, CS_ERR_NOT_READY, "cs_sky_create: textures and transmittance LUT first");
+    if (s->frames_to_update < 1) return fail(c, CS_ERR_INVALID, "frames_to_update must be >= 1");
+    cs_sky* k = new cs_sky();
+    k->c = c; k->s = *s;
+    cs_frame_state_init(&k->fd);
+    for (auto& l : k->luts) l.assign((size_t)CS_SKY_LUT_W * CS_SKY_LUT_H * 4, 0);
+    sky_alloc(k);
+    *out = k;
+    return CS_OK;
+}
+void cs_sky_destroy(cs_sky* k) { delete k; }
+int cs_sky_set_settings(cs_sky* k, const cs_sky_settings* s) {
+    if (!k || !s) return CS_ERR_INVALID;
+    if (s->frames_to_update < 1) return fail(k->c, CS_ERR_INVALID, "frames_to_update must be >= 1");
+    bool rebuild = s->texture_size != k->s.texture_size || s->frames_to_update != k->s.frames_to_update;
+    k->s = *s;
+    if (rebuild) {  // cloud_sky.gd:37-50,197-212
+        k->frame = 0; k->tex_update = 0; k->tex_from = 1; k->tex_to = 2; k->pos[0] = k->pos[1] = 0;
+        sky_alloc(k);
+        k->full_init = true;
+    }
+    return CS_OK;
+}
+int cs_sky_set_sun(cs_sky* k, const float b[9], float e, const float col[3]) {
+    if (!k || !b || !col) return CS_ERR_INVALID;
+    memcpy(k->basis, b, 36); k->energy = e; memcpy(k->color, col, 12);
+    if (!k->sun_attached) k->full_init = true;  // sun.gd:11-13
+    k->sun_attached = true;
+    return CS_OK;
+}
+int cs_sky_update(cs_sky* k, float now) { return k ? sky_tick(k, now) : CS_ERR_INVALID; }
+int cs_sky_get_frame(cs_sky* k, cs_sky_frame* o) {
+    if (!k || !o) return CS_ERR_INVALID;
+    memset(o, 0, sizeof(*o));
+    o->frame = k->frame; o->frames_to_update = k->s.frames_to_update; o->texture_size = k->size;
+    o->update_position[0] = k->pos[0]; o->update_position[1] = k->pos[1];
+    o->update_region_size = k->region; o->num_workgroups = k->groups;
+    o->texture_to_update = k->tex_update; o->texture_to_blend_from = k->tex_from; o->texture_to_blend_to = k->tex_to;
+    o->blend_amount = k->blend;
+    o->sky_current_texture = k->lut_current; o->sky_blend_from = k->lut_current; o->sky_blend_to = (k->lut_current + 1) % 3;
+    o->sky_updates = k->lut_updates;
+    for (int i = 0; i < 3; i++) { o->cloud_textures[i] = k->textures[i].data(); o->sky_luts[i] = k->luts[i].data(); }
+    o->frame_data = k->fd;
+    return CS_OK;
+}
+int cs_sky_read_texture(cs_sky* k, int i, uint16_t* out, size_t bytes) {
+    if (!k || !out || i < 0 || i > 2 || bytes != k->textures[i].size() * 2) return CS_ERR_INVALID;
+    memcpy(out, k->textures[i].data(), bytes);
+    return CS_OK;
+}
+
+// ---- presentation composite: clouds.gdshader -----------------------------------------------------------------
+}  // extern "C" (reopened below)
+
+namespace {
+const float GD_PI = 3.14159265358979323846f;  // Godot shading language PI
+
+// bilinear CLAMP_TO_EDGE fetch of an RGBA16F texture (filter_linear, repeat_disable: clouds.gdshader:4-10)
+V4 sample_half4_clamp(const uint16_t* t, int w, int h, float u, float v) { return sample_lut(t, w, h, u, v); }
+
+// clouds.gdshader:15-32
+V2 gd_vec3_to_oct(V3 e) {
+    float s = fabsf(e.x) + fabsf(e.y) + fabsf(e.z);
+    e = e / s;
+    if (!(e.z >= 0.0f)) {
+        float sx = e.x >= 0.0f ? 1.0f : -1.0f, sy = e.y >= 0.0f ? 1.0f : -1.0f;
+        float wx = (1.0f - fabsf(e.y)) * sx, wy = (1.0f - fabsf(e.x)) * sy;
+        e.x = wx; e.y = wy;
+    }
+    V2 n;
+    n.y = e.y * 0.5f + 0.5f;
+    n.x = e.x * 0.5f + n.y;
+    n.y = e.x * -0.5f + n.y;
+    return n;
+}
+// clouds.gdshader:34-45
+V3 gd_sky_lut(const uint16_t* from, const uint16_t* to, float blend, V3 d) {
+    float phi = atan2f(d.z, d.x), theta = asinf(d.y);
+    float u = (phi / GD_PI * 0.5f + 0.5f);
+    float v = sqrtf(fabsf(theta) / (GD_PI * 0.5f)) * signf(theta) * 0.5f + 0.5f;
+    V4 a = sample_half4_clamp(from, CS_SKY_LUT_W, CS_SKY_LUT_H, u, v), b = sample_half4_clamp(to, CS_SKY_LUT_W, CS_SKY_LUT_H, u, v);
+    V3 m = mix3({a.x, a.y, a.z}, {b.x, b.y, b.z}, blend);
+    return m / 50.0f;
+}
+// clouds.gdshader:48-59
+float gd_sun_with_bloom(V3 ray, V3 sun, float disk_scale) {
+    float sunSolidAngle = disk_scale * 0.53f * GD_PI / 180.0f;
+    float minSunCosTheta = cosf(sunSolidAngle);
+    float cosTheta = dot3(ray, sun);
+    if (cosTheta >= minSunCosTheta) return 1.0f;
+    float offset = minSunCosTheta - cosTheta;
+    float gaussianBloom = expf(-offset * 50000.0f) * 0.5f;
+    float invBloom = 1.0f / (0.02f + offset * 300.0f) * 0.01f;
+    return gaussianBloom + invBloom;
+}
+// clouds.gdshader:61-71
+float gd_ray_intersect_sphere(V3 ro, V3 rd, float rad) {
+    float b = dot3(ro, rd);
+    float c = dot3(ro, ro) - rad * rad;
+    if (c > 0.0f && b > 0.0f) return -1.0f;
+    float discr = b * b - c;
+    if (discr < 0.0f) return -1.0f;
+    if (discr > b * b) return (-b + sqrtf(discr));
+    return -b - sqrtf(discr);
+}
+// clouds.gdshader:87-102
+V3 gd_get_atmo(const uint16_t* sky_from, const uint16_t* sky_to, const uint16_t* tlut, float blend, V3 dir, V3 sun, float disk_scale) {
+    const float groundRadiusMM = 6.360f, atmosphereRadiusMM = 6.460f;
+    const V3 viewPos = {0.0f, groundRadiusMM + 0.0002f, 0.0f};
+    V3 col = gd_sky_lut(sky_from, sky_to, blend, dir);
+    float sl = smoothstepf(0.002f, 1.0f, gd_sun_with_bloom(dir, sun, disk_scale));
+    V3 sunLum = {sl, sl, sl};
+    if (length3(sunLum) > 0.0f) {
+        if (gd_ray_intersect_sphere(viewPos, dir, groundRadiusMM) >= 0.0f) {
+            sunLum = sunLum * 0.0f;
+        } else {  // getValFromTLUT (:77-85)
+            float height = length3(viewPos);
+            V3 up = viewPos / height;
+            float c = dot3(up, sun);
+            float u = 256.0f * clampf(0.5f + 0.5f * c, 0.0f, 1.0f) / 256.0f;
+            float v = 64.0f * fmaxf(0.0f, fminf(1.0f, (height - groundRadiusMM) / (atmosphereRadiusMM - groundRadiusMM))) / 64.0f;
+            V4 t = sample_half4_clamp(tlut, CS_TRANSMITTANCE_W, CS_TRANSMITTANCE_H, u, v);
+            sunLum = sunLum * V3{t.x, t.y, t.z};
+        }
+    }
+    return col + sunLum;
+}
+V3 view_direction(const cs_view& vw, int x, int y) {
+    if (vw.projection == CS_VIEW_EQUIRECT) {
+        float a = ((float)x + 0.5f) / (float)vw.width * (2.0f * GD_PI) - GD_PI;
+        float e = GD_PI * 0.5f - ((float)y + 0.5f) / (float)vw.height * GD_PI;
+        return {sinf(a) * cosf(e), sinf(e), -cosf(a) * cosf(e)};
+    }
+    float th = tanf(vw.fov_y_degrees * (GD_PI / 180.0f) * 0.5f);
+    float nx = (((float)x + 0.5f) / (float)vw.width * 2.0f - 1.0f) * th * ((float)vw.width / (float)vw.height);
+    float ny = (1.0f - ((float)y + 0.5f) / (float)vw.height * 2.0f) * th;
+    const float* b = vw.basis_columns;
+    V3 d = {b[0] * nx + b[3] * ny - b[6], b[1] * nx + b[4] * ny - b[7], b[2] * nx + b[5] * ny - b[8]};
+    return normalize3(d);
+}
+// sky() (clouds.gdshader:104-116)
+V3 gd_sky_pixel(const cs_view& vw, const uint16_t* cf, const uint16_t* ct, int tw, int th, const uint16_t* sf, const uint16_t* st,
+                const uint16_t* tlut, V3 eyedir) {
+    V3 norm = eyedir;
+    norm.y = fmaxf(0.0f, norm.y);
+    norm = normalize3(norm);
+    V2 uv = gd_vec3_to_oct({norm.x, norm.z, norm.y});
+    V4 a = sample_half4_clamp(cf, tw, th, uv.x, uv.y), b = sample_half4_clamp(ct, tw, th, uv.x, uv.y);
+    float k = vw.blend_amount;
+    V4 clouds = {mixf(a.x, b.x, k), mixf(a.y, b.y, k), mixf(a.z, b.z, k), mixf(a.w, b.w, k)};
+    V3 sun = {vw.sun_direction[0], vw.sun_direction[1], vw.sun_direction[2]};
+    V3 background = gd_get_atmo(sf, st, tlut, k, eyedir, sun, vw.sun_disk_scale);
+    V3 color = background * (1.0f - clouds.w) + V3{clouds.x, clouds.y, clouds.z};
+    float f = smoothstepf(0.6f, 1.0f, 1.0f - eyedir.y);
+    auto cl = [](float v) { return clampf(v, 0.0f, 100.0f); };
+    return mix3({cl(color.x), cl(color.y), cl(color.z)}, {cl(background.x), cl(background.y), cl(background.z)}, f);
+}
+}  // namespace
+
+extern "C" {
+
+int cs_composite(cs_context* c, const cs_view* vw, const void* cf, const void* ct, int tw, int th, const void* sf, const void* st, float* out) {
+    if (!c || !vw || !cf || !ct || !sf || !st || !out) return CS_ERR_INVALID;
+    if (!c->have_tlut) return fail(c, CS_ERR_NOT_READY, "cs_composite: build the transmittance LUT first");
+    if (vw->width < 1 || vw->height < 1 || tw < 1 || th < 1 || (vw->projection != CS_VIEW_EQUIRECT && vw->projection != CS_VIEW_PERSPECTIVE))
+        return fail(c, CS_ERR_INVALID, "cs_composite: bad view");
+    parallel_rows(c->threads, vw->height, [&](int y, int) {
+        for (int x = 0; x < vw->width; x++) {
+            V3 col = gd_sky_pixel(*vw, (const uint16_t*)cf, (const uint16_t*)ct, tw, th, (const uint16_t*)sf, (const uint16_t*)st, c->tlut.data(), view_direction(*vw, x, y));
+            float* o = out + ((size_t)y * vw->width + x) * 4;
+            o[0] = col.x; o[1] = col.y; o[2] = col.z; o[3] = 1.0f;
+        }
+    });
+    return CS_OK;
+}
+int cs_sky_composite_host(cs_sky* k, const cs_view* vw, float* out, size_t bytes) {
+    if (!k || !vw || !out) return CS_ERR_INVALID;
+    if (bytes != (size_t)vw->width * vw->height * 16) return fail(k->c, CS_ERR_INVALID, "cs_sky_composite_host: bad buffer size");
+    cs_view v = *vw;
+    v.blend_amount = k->blend;
+    return cs_composite(k->c, &v, k->textures[k->tex_from].data(), k->textures[k->tex_to].data(), k->size, k->size,
+                        k->luts[k->lut_current].data(), k->luts[(k->lut_current + 1) % 3].data(), out);
+}
+
 // ---- oracle-only probes for the known-answer tests (tests/test_oracle_known_answers.py) --------
 // Not part of include/cloudsky.h; they expose the internal functions of the restatement so that
 // each can be pinned against an analytic answer derived from the shader source.
