@@ -453,6 +453,11 @@ class Sky:
         self.ctx = ctx
         self._h = _P()
         ctx._ck(ctx.lib.dll.cs_sky_create(ctx._h, C.byref(settings), C.byref(self._h)))
+        self._sync_size()
+
+    def _sync_size(self) -> None:
+        n = self.frame().texture_size  # the library resizes the context's image with the sky (update_performance)
+        self.ctx.width = self.ctx.height = n
 
     def close(self) -> None:
         if getattr(self, "_h", None):
@@ -461,6 +466,7 @@ class Sky:
 
     def set_settings(self, settings: SkySettings) -> None:
         self.ctx._ck(self.ctx.lib.dll.cs_sky_set_settings(self._h, C.byref(settings)))
+        self._sync_size()
 
     def set_sun(self, basis_columns, energy: float, color_srgb) -> None:
         b = (C.c_float * 9)(*[float(v) for v in basis_columns])
