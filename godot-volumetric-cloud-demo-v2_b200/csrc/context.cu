@@ -231,21 +231,25 @@ int upload_levels(cs_context* c, const std::vector<uint8_t>& large0, int ln, con
     for (int l = 0; l < c->large_levels && half_ok; l++) half_ok = pack_large_h(c->h_large[l], ln >> l, lh[l]);
     for (int l = 0; l < c->small_levels && half_ok; l++) half_ok = pack_small_h(c->h_small[l], sn >> l, sh[l]);
     if (half_ok) half_ok = pack_weather_h(weather, ww, wh, wh16);
-    c->records_half = half_ok ? 1 : 0;
+    // format mask: bit 0 large, bit 1 small, bit 2 weather.  All-half when exact; CLOUDSKY_RECORDS=1|3|7 (development knob)
+    // selects the mixed layouts measured in DESIGN.md.
+    int fmt = half_ok ? 7 : 0;
+    if (half_ok && getenv("CLOUDSKY_RECORDS")) { int v = atoi(getenv("CLOUDSKY_RECORDS")); if (v == 1 || v == 3 || v == 7) fmt = v; }
+    c->records_half = fmt;
     auto put = [&](float** dst, const void* src, size_t bytes) -> cudaError_t {
         cudaError_t e = cudaMalloc(dst, bytes);
         return e != cudaSuccess ? e : cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
     };
     std::vector<float> pk;
     for (int l = 0; l < c->large_levels; l++) {
-        if (half_ok) { CU(put(&c->d_large_f[l], lh[l].data(), lh[l].size() * 2)); }
+        if (fmt & 1) { CU(put(&c->d_large_f[l], lh[l].data(), lh[l].size() * 2)); }
         else { pack_large_f(c->h_large[l], ln >> l, pk); CU(put(&c->d_large_f[l], pk.data(), pk.size() * 4)); }
     }
     for (int l = 0; l < c->small_levels; l++) {
-        if (half_ok) { CU(put(&c->d_small_f[l], sh[l].data(), sh[l].size() * 2)); }
+        if (fmt & 2) { CU(put(&c->d_small_f[l], sh[l].data(), sh[l].size() * 2)); }
         else { pack_small_f(c->h_small[l], sn >> l, pk); CU(put(&c->d_small_f[l], pk.data(), pk.size() * 4)); }
     }
-    if (half_ok) { CU(put(&c->d_weather_f, wh16.data(), wh16.size() * 2)); }
+    if (fmt & 4) { CU(put(&c->d_weather_f, wh16.data(), wh16.size() * 2)); }
     else { pack_weather_f(weather, ww, wh, pk); CU(put(&c->d_weather_f, pk.data(), pk.size() * 4)); }
     c->have_tex = true;
     return CS_OK;

@@ -46,7 +46,7 @@ struct CloudLaunch {
     int large_shift, small_shift, weather_shx, weather_shy;  // log2 of the level-0 edges
     float large_fn0, small_fn0, weather_fw, weather_fh;   // level-0 texels per metre (edge * texture scale) and weather edges, used straight from the constant bank
     int large_mask0, small_mask0, weather_maskx, weather_masky;
-    int records_half;     // 1: large_f/small_f/weather_f hold exact-integer fp16 records (32/16/16 B), 0: fp32 records (64/32/32 B)
+    int records_half;     // format mask: bit 0 large_f, bit 1 small_f, bit 2 weather_f; set = fp16 records (32/16/16 B), clear = fp32 (64/32/32 B)
     int variant;          // development variant of the fast kernel (0 = production)
     int weather_type_hi;  // 1 when every weather texel has R >= 128 (cloud type >= 0.5): affine height-gradient fast path
     const float* large_f[kMaxLargeLevels];  // 64 B per texel: 8 trilinear coefficients of R, then 8 of fbm
