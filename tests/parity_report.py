@@ -2,7 +2,7 @@
 """Parity margins of the CUDA path against the CPU oracle (test infrastructure) on a 256x128 frame: pass
 fraction at the stated tolerances and error percentiles, for the DESIGN.md table."""
 import json, os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # tests/ -> repo root
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 import cloudsky_b200 as cs
