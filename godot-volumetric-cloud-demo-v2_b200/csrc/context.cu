@@ -277,7 +277,6 @@ int make_launch(cs_context* c, const cs_cloud_params* P, int x0, int y0, int x1,
     L.large_shift = ilog2(c->large_n); L.small_shift = ilog2(c->small_n);
     L.weather_shx = ilog2(c->weather_w); L.weather_shy = ilog2(c->weather_h);
     L.weather_type_hi = c->weather_type_hi;
-    L.variant = c->variant;
     L.records_half = c->records_half;
     // texels per metre at level 0 (exact: power-of-two edge times the shader's texture scale, clouds.glsl:117,132)
     L.large_fn0 = (float)c->large_n * 0.00008f; L.small_fn0 = (float)c->small_n * 0.001f;
@@ -539,11 +538,9 @@ int cs_resize(cs_context* c, int w, int h) {
 }
 int cs_set_march_config(cs_context* c, int p, int cone, int mode) {
     if (!c) return CS_ERR_INVALID;
-    int variant = (mode >> 8) & 0xff;  // development knob: fast-kernel variant, 0 = production
-    mode &= 0xff;
     if (p < 1 || p > 4096 || cone < 0 || cone > 64 || (mode != CS_MODE_FAST && mode != CS_MODE_STRICT))
         return fail(c, CS_ERR_INVALID, "cs_set_march_config: primary_steps in [1,4096], cone_samples in [0,64], mode FAST|STRICT");
-    c->primary_steps = p; c->cone_samples = cone; c->mode = mode; c->variant = variant;
+    c->primary_steps = p; c->cone_samples = cone; c->mode = mode;
     return CS_OK;
 }
 int cs_set_counters_enabled(cs_context* c, int on) {

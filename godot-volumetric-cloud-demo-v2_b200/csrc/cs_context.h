@@ -43,7 +43,7 @@ struct cs_context {
     unsigned async_frame = 0;
 
     // march config
-    int primary_steps = CS_REF_PRIMARY_STEPS, cone_samples = CS_REF_CONE_SAMPLES, mode = CS_MODE_FAST, variant = 0;
+    int primary_steps = CS_REF_PRIMARY_STEPS, cone_samples = CS_REF_CONE_SAMPLES, mode = CS_MODE_FAST;
     bool counters_on = false;
     unsigned long long* d_counters = nullptr;
 

@@ -47,7 +47,6 @@ struct CloudLaunch {
     float large_fn0, small_fn0, weather_fw, weather_fh;   // level-0 texels per metre (edge * texture scale) and weather edges, used straight from the constant bank
     int large_mask0, small_mask0, weather_maskx, weather_masky;
     int records_half;     // format mask: bit 0 large_f, bit 1 small_f, bit 2 weather_f; set = fp16 records (32/16/16 B), clear = fp32 (64/32/32 B)
-    int variant;          // development variant of the fast kernel (0 = production)
     int weather_type_hi;  // 1 when every weather texel has R >= 128 (cloud type >= 0.5): affine height-gradient fast path
     const float* large_f[kMaxLargeLevels];  // 64 B per texel: 8 trilinear coefficients of R, then 8 of fbm
     const float* small_f[kMaxSmallLevels];  // 32 B per texel: 8 trilinear coefficients of hfbm
