@@ -201,7 +201,7 @@ def test_generalised_step_counts(cs, pair, helpers, oracle_lib, product_lib):
     o, g, W, H = pair
     p = helpers.make_params(product_lib, W, H)
     o.build_sky_lut((0, 1, 0)); g.write_sky_lut(o.read_sky_lut())
-    for P, Lc in ((32, 3), (64, 5), (128, 7), (48, 11)):
+    for P, Lc in ((32, 3), (64, 5), (128, 7), (48, 11), (16, 20), (24, 0)):  # 20 cone samples: beyond the cooperative tables; 0: distant sample only
         o.set_march_config(P, Lc)
         o.render_frame(p)
         ref = o.read_image()
@@ -209,7 +209,11 @@ def test_generalised_step_counts(cs, pair, helpers, oracle_lib, product_lib):
             g.set_march_config(P, Lc, mode)
             g.render_frame(p)
             frac, mx = helpers.compare_images(g.read_image(), ref, tol[0], tol[1])
-            assert frac >= tol[2], (P, Lc, mode, frac, mx)
+            # 16-24 primary steps: one lit/unlit flip of a single sample is 1/16 of the pixel, so the fast kernel's
+            # rounding noise crosses the tolerance on more pixels (measured 99.45 %, independent of the cone count;
+            # the strict kernel stays at 100 %)
+            need = tol[2] if (P >= 32 or mode == cs.MODE_STRICT) else 0.99
+            assert frac >= need, (P, Lc, mode, frac, mx)
     o.set_march_config(128, 6)
     g.set_march_config(128, 6, cs.MODE_FAST)
 
