@@ -205,9 +205,9 @@ def ncu_traffic():
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_latest.json")) as f:
             d = json.load(f)
-        return d.get("dram_bytes_per_launch"), d.get("source")
+        return d.get("dram_bytes_per_launch"), d.get("source"), {k: d.get(k) for k in ("l2_hit_pct", "l1_hit_pct", "issue_active_pct")}
     except Exception:
-        return None, None
+        return None, None, {}
 
 
 def run_ours(args):
@@ -306,10 +306,15 @@ def run_ours(args):
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     kt = ctx.read_kernel_timings()
     ctx.set_kernel_timing(False)
+    per_rank_kernel_ms = [round((kt["march_ms"] + kt["sky_ms"]) / max(1, kt["march_launches"]), 4)]
     if dist is not None:
         t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_ms = float(t.item())
+        mine_ms = torch.tensor([per_rank_kernel_ms[0]], dtype=torch.float64, device="cuda")
+        all_ms = torch.zeros(world, dtype=torch.float64, device="cuda")
+        dist.all_gather_into_tensor(all_ms, mine_ms)
+        per_rank_kernel_ms = [round(float(v), 4) for v in all_ms.tolist()]
 
     ray_steps_per_frame = counters["marched_pixels"] * PRIMARY
     value = world * ray_steps_per_frame * args.steps / (dev_ms * 1e-3) / 1e6
@@ -350,10 +355,10 @@ def run_ours(args):
     alg_bytes = 80 * counters["density_evals"] + 8 * W * H  # 80 B per density evaluation + 8 B per pixel
     march_ms = kt["march_ms"] / max(1, kt["march_launches"])
     achieved = alg_bytes / (march_ms * 1e-3) / 1e9
-    traffic, traffic_src = ncu_traffic()
+    traffic, traffic_src, ncu_extra = ncu_traffic()
     roofline = {"bound": "hbm", "kernel": "clouds_fast_kernel", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                "kernel_ms": round(march_ms, 4), "algorithmic_bytes_per_launch": alg_bytes,
+                "kernel_ms": round(march_ms, 4), "algorithmic_bytes_per_launch": alg_bytes, "ncu": ncu_extra,
                 "note": "algorithmic bytes = 80 B x executed density evaluations + 8 B x pixels (SURVEY 8(d)); the texel working set is L1/L2-resident, "
                         "so DRAM traffic is far below this figure and frac can exceed 1"}
     cpu_threads = os.cpu_count() or 1
@@ -369,7 +374,9 @@ def run_ours(args):
             "roofline": roofline, "e2e": e2e, "gpu_launches": 3 * args.steps,
             "kernels": {"march_ms_avg": round(march_ms, 4), "sky_lut_ms_avg": round(kt["sky_ms"] / max(1, kt["sky_launches"]), 4)},
             "gevals_per_s": round(world * counters["density_evals"] * args.steps / (dev_ms * 1e-3) / 1e9, 2),
-            "wall_ms_per_step_incl_flush": round(1e3 * t_wall / args.steps, 3), "clocks": clocks}
+            "wall_ms_per_step_incl_flush": round(1e3 * t_wall / args.steps, 3), "clocks": clocks,
+            "per_rank_kernel_ms": per_rank_kernel_ms,  # sky LUT + march per step on every rank (load balance)
+            "value_without_gather": round(world * ray_steps_per_frame / (max(per_rank_kernel_ms) * 1e-3) / 1e6, 1)}
     if cpu_v is not None:
         line["cpu_baseline"] = {"value": round(cpu_v, 3), "unit": UNIT, "cores": cpu_threads, "kind": "port", "sample": cpu_sample}
     print(json.dumps(line), flush=True)

@@ -45,7 +45,9 @@ def main():
     json.dump(summary, open(out, "w"), indent=1)
     if kernels:
         k = kernels[-1]
-        json.dump({"dram_bytes_per_launch": k["dram_bytes"], "kernel": k["kernel"], "source": f"{out} (ncu --set full --clock-control none: dram__bytes_read.sum + dram__bytes_write.sum)"},
+        hit = lambda name: float(k["metrics"][name]["value"]) if name in k["metrics"] else None
+        json.dump({"dram_bytes_per_launch": k["dram_bytes"], "kernel": k["kernel"], "l2_hit_pct": hit("lts__t_sector_hit_rate.pct"),
+                   "l1_hit_pct": hit("l1tex__t_sector_hit_rate.pct"), "issue_active_pct": hit("smsp__issue_active.avg.pct_of_peak_sustained_active"), "source": f"{out} (ncu --set full --clock-control none: dram__bytes_read.sum + dram__bytes_write.sum)"},
                   open("profiles/roofline_latest.json", "w"), indent=1)
     print(json.dumps({k["kernel"]: k["dram_bytes"] for k in kernels}))
 
