@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <new>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -403,9 +404,17 @@ int cs_sync(cs_context* c) {
 }
 int cs_set_threads(cs_context* c, int) { return c ? CS_OK : CS_ERR_INVALID; }
 
+// The C ABI never lets a C++ exception escape: allocation failures of the host-side staging buffers become error codes.
+#define CS_GUARD_BEGIN try {
+#define CS_GUARD_END(ctx)                                                                    \
+    }                                                                                        \
+    catch (const std::bad_alloc&) { return fail(ctx, CS_ERR_INVALID, "out of host memory"); } \
+    catch (...) { return fail(ctx, CS_ERR_INVALID, "unexpected C++ exception"); }
+
 int cs_upload_textures(cs_context* c, const uint8_t* large, int ln, int lch, const uint8_t* small, int sn, int sch,
                        const uint8_t* weather, int ww, int wh, int wch) {
     if (!c) return CS_ERR_INVALID;
+    CS_GUARD_BEGIN
     if (!large || !small || !weather || ln < 1 || sn < 1 || ww < 1 || wh < 1 || lch < 3 || lch > 4 || sch < 3 || sch > 4 || wch < 3 || wch > 4)
         return fail(c, CS_ERR_INVALID, "cs_upload_textures: null pointer or bad dimensions / channel count");
     std::vector<uint8_t> l0, s0, w0;
@@ -413,11 +422,13 @@ int cs_upload_textures(cs_context* c, const uint8_t* large, int ln, int lch, con
     expand_rgba(small, (size_t)sn * sn * sn, sch, s0);
     expand_rgba(weather, (size_t)ww * wh, wch, w0);
     return upload_levels(c, l0, ln, s0, sn, w0, ww, wh);
+    CS_GUARD_END(c)
 }
 
 int cs_load_texture_files(cs_context* c, const char* large_path, int large_slices, const char* small_path, int small_slices,
                           const char* weather_path) {
     if (!c) return CS_ERR_INVALID;
+    CS_GUARD_BEGIN
     HostImage li, si, wi;
     std::string e = decode_image_file(large_path, li);
     if (!e.empty()) return fail(c, CS_ERR_IO, e);
@@ -433,18 +444,23 @@ int cs_load_texture_files(cs_context* c, const char* large_path, int large_slice
     if (!e.empty()) return fail(c, CS_ERR_IO, std::string(small_path) + ": " + e);
     expand_rgba(wi.px.data(), (size_t)wi.w * wi.h, wi.ch, w0);
     return upload_levels(c, l0, ln, s0, sn, w0, wi.w, wi.h);
+    CS_GUARD_END(c)
 }
 
 int cs_decode_image_file(const char* path, uint8_t** out_pixels, int* w, int* h, int* ch) {
     if (!path || !out_pixels || !w || !h || !ch) return CS_ERR_INVALID;
-    HostImage im;
-    std::string e = decode_image_file(path, im);
-    if (!e.empty()) return CS_ERR_IO;
-    uint8_t* p = (uint8_t*)malloc(im.px.size());
-    if (!p) return CS_ERR_IO;
-    memcpy(p, im.px.data(), im.px.size());
-    *out_pixels = p; *w = im.w; *h = im.h; *ch = im.ch;
-    return CS_OK;
+    try {
+        HostImage im;
+        std::string e = decode_image_file(path, im);
+        if (!e.empty()) return CS_ERR_IO;
+        uint8_t* p = (uint8_t*)malloc(im.px.size());
+        if (!p) return CS_ERR_IO;
+        memcpy(p, im.px.data(), im.px.size());
+        *out_pixels = p; *w = im.w; *h = im.h; *ch = im.ch;
+        return CS_OK;
+    } catch (...) {
+        return CS_ERR_IO;
+    }
 }
 void cs_free(void* p) { free(p); }
 
