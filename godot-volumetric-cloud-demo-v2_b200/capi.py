@@ -19,6 +19,7 @@ PRODUCT_LIB = os.path.join(PKG_DIR, "csrc", "libcloudsky_b200.so")
 CS_OK = 0
 MODE_FAST = 0
 MODE_STRICT = 1
+MODE_EARLY_OUT = 2  # flag for MODE_FAST: stop a ray once T < 2^-12 (not reference behaviour)
 TRANSMITTANCE_W, TRANSMITTANCE_H = 256, 64  # transmittance_lut.gd:6
 SKY_LUT_W, SKY_LUT_H = 200, 100  # sky_lut.gd:4
 REF_PRIMARY_STEPS, REF_CONE_SAMPLES = 128, 6  # clouds.glsl:228, :186

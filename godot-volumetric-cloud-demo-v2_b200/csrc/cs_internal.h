@@ -34,6 +34,7 @@ struct CloudLaunch {
     int width, height;        // image size (== P.texture_size)
     int x0, y0, x1, y1;       // pixel rectangle to render (already clipped)
     int out_pitch_px;         // row pitch of out, in pixels
+    float early_out_T;        // 0: run every primary step like the reference; > 0: CS_MODE_EARLY_OUT transmittance threshold
     int primary_steps;        // 128 in the reference
     int cone_samples;         // 6 in the reference
     int large_n, large_levels;

@@ -110,6 +110,11 @@ typedef struct cs_counters {
 /* march mode flags for cs_set_march_config */
 #define CS_MODE_FAST 0   /* product kernel: FMA contraction, fast intrinsics, exact-zero skips */
 #define CS_MODE_STRICT 1 /* same operation order as the oracle, --fmad=false, IEEE div/sqrt  */
+/* Optional flag for CS_MODE_FAST (mode = CS_MODE_FAST | CS_MODE_EARLY_OUT), NOT reference behaviour (the reference runs all
+ * primary steps even after T ~ 0, clouds.glsl:172): stop marching a ray once its transmittance T < 2^-12.  alpha = 1 - T
+ * then already rounds to 1.0 in fp16 and the skipped radiance is below one fp16 ulp; executed (not nominal) primary steps
+ * are reported by the counters.  Pays off for overcast skies (BASELINE config 5). */
+#define CS_MODE_EARLY_OUT 2
 
 /* ---- lifetime -------------------------------------------------------------------------- */
 

@@ -190,6 +190,32 @@ def test_odd_sizes_and_partial_tiles(cs, helpers, oracle_lib, product_lib, textu
         o.close(); g.close()
 
 
+def test_early_out_mode(cs, pair, helpers, oracle_lib, product_lib):
+    """CS_MODE_FAST | CS_MODE_EARLY_OUT (opt-in, not reference behaviour): rays stop once T < 2^-12.  alpha is unchanged
+    (it already rounds to 1.0 in fp16), RGB moves by at most a couple of fp16 ulps, the oracle tolerance still holds,
+    and overcast skies execute far fewer primary steps."""
+    o, g, W, H = pair
+    for cov, min_saving in ((1.0, 0.2), (0.2, 0.0)):
+        p = helpers.make_params(product_lib, W, H, coverage=cov, density=0.1 if cov == 1.0 else None)
+        o.set_march_config(128, 6); o.build_sky_lut(tuple(p.light_direction)); o.render_frame(p)
+        ref = o.read_image()
+        g.write_sky_lut(o.read_sky_lut())
+        g.set_counters_enabled(True)
+        g.set_march_config(128, 6, cs.MODE_FAST); g.render_frame(p)
+        full, k_full = g.read_image(), g.get_counters().as_dict()
+        g.set_march_config(128, 6, cs.MODE_FAST | cs.MODE_EARLY_OUT); g.render_frame(p)
+        early, k_early = g.read_image(), g.get_counters().as_dict()
+        g.set_counters_enabled(False)
+        assert (early[..., 3].view(np.uint16) == full[..., 3].view(np.uint16)).all()              # alpha bit-identical
+        d = np.abs(early[..., :3].view(np.int16).astype(np.int32) - full[..., :3].view(np.int16).astype(np.int32))
+        assert d.max() <= 2, d.max()                                                              # <= 2 fp16 ulps in RGB
+        frac, mx = helpers.compare_images(early, ref, 2e-3, 1e-2)
+        assert frac >= 0.999, (cov, frac, mx)
+        assert k_early["primary_steps"] <= k_full["primary_steps"] * (1.0 - min_saving), (cov, k_early["primary_steps"], k_full["primary_steps"])
+        assert k_full["primary_steps"] == k_full["marched_pixels"] * 128                          # nominal steps without the flag
+    g.set_march_config(128, 6, cs.MODE_FAST)
+
+
 def test_counters_match_oracle(cs, pair, helpers, oracle_lib, product_lib):
     o, g, W, H = pair
     p = helpers.make_params(product_lib, W, H)

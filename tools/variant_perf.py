@@ -22,7 +22,7 @@ def main():
         p = lib.fill_cloud_params(s, st, W, H)
         ref = None
         for v in variants:
-            ctx.set_march_config(P, cone, cs.MODE_FAST)
+            ctx.set_march_config(P, cone, cs.MODE_FAST | (cs.MODE_EARLY_OUT if v == 1 else 0))  # variant 1 = early-out flag
             ms = min(ctx.time_render_frame(p, 2, 5) for _ in range(3))
             ctx.render_frame(p)
             img = ctx.read_image()
