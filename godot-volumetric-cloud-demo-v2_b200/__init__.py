@@ -7,9 +7,9 @@ Import name: ``cloudsky_b200`` (see cloudsky_b200.py at the repo root; the direc
 """
 from . import capi  # noqa: F401
 from .capi import (CloudParams, CloudSkyError, Context, Counters, FrameState, Library, Sky, SkyFrame, SkySettings, View,  # noqa: F401
-                   MODE_EARLY_OUT, MODE_FAST, MODE_STRICT, load_product)
+                   MODE_EARLY_OUT, MODE_FAST, MODE_STRICT, MODE_TEX, load_product)
 
 from .sky import CloudSky, DirectionalLight, SkyLUT, TransmittanceLUT  # noqa: F401,E402
 
 __all__ = ["CloudSky", "DirectionalLight", "SkyLUT", "TransmittanceLUT", "capi", "CloudParams", "CloudSkyError", "Context", "Counters", "FrameState", "Library", "Sky", "SkyFrame", "SkySettings", "View",
-           "MODE_EARLY_OUT", "MODE_FAST", "MODE_STRICT", "load_product"]
+           "MODE_EARLY_OUT", "MODE_FAST", "MODE_STRICT", "MODE_TEX", "load_product"]

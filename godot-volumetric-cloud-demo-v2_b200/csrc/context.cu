@@ -50,7 +50,61 @@ void free_textures(cs_context* c) {
     if (c->d_weather) cudaFree(c->d_weather);
     if (c->d_weather_f) cudaFree(c->d_weather_f);
     c->d_weather = nullptr; c->d_weather_f = nullptr;
+    if (c->t_large) cudaDestroyTextureObject(c->t_large);
+    if (c->t_small) cudaDestroyTextureObject(c->t_small);
+    if (c->t_weather) cudaDestroyTextureObject(c->t_weather);
+    if (c->a_large) cudaFreeMipmappedArray(c->a_large);
+    if (c->a_small) cudaFreeMipmappedArray(c->a_small);
+    if (c->a_weather) cudaFreeArray(c->a_weather);
+    c->t_large = c->t_small = c->t_weather = 0;
+    c->a_large = c->a_small = nullptr; c->a_weather = nullptr;
     c->have_tex = false;
+}
+
+// CS_MODE_TEX: the RGBA8 mip chain of a volume as a CUDA mipmapped 3D array behind a texture object with the reference's
+// sampler state (REPEAT, linear filter inside a level; the kernel names the level itself, like textureLod()).
+cudaError_t make_volume_texture(const std::vector<std::vector<uint8_t>>& levels, int n, cudaMipmappedArray_t* arr, cudaTextureObject_t* tex) {
+    cudaChannelFormatDesc fd = cudaCreateChannelDesc<uchar4>();
+    cudaError_t e = cudaMallocMipmappedArray(arr, &fd, make_cudaExtent(n, n, n), (unsigned)levels.size(), 0);
+    if (e != cudaSuccess) return e;
+    for (size_t l = 0; l < levels.size(); l++) {
+        int nl = n >> l;
+        cudaArray_t lvl = nullptr;
+        if ((e = cudaGetMipmappedArrayLevel(&lvl, *arr, (unsigned)l)) != cudaSuccess) return e;
+        cudaMemcpy3DParms cp = {};
+        cp.srcPtr = make_cudaPitchedPtr(const_cast<uint8_t*>(levels[l].data()), (size_t)nl * 4, nl, nl);
+        cp.dstArray = lvl;
+        cp.extent = make_cudaExtent(nl, nl, nl);
+        cp.kind = cudaMemcpyHostToDevice;
+        if ((e = cudaMemcpy3D(&cp)) != cudaSuccess) return e;
+    }
+    cudaResourceDesc rd = {};
+    rd.resType = cudaResourceTypeMipmappedArray;
+    rd.res.mipmap.mipmap = *arr;
+    cudaTextureDesc td = {};
+    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeWrap;
+    td.filterMode = cudaFilterModeLinear;
+    td.mipmapFilterMode = cudaFilterModePoint;
+    td.readMode = cudaReadModeNormalizedFloat;
+    td.normalizedCoords = 1;
+    td.minMipmapLevelClamp = 0.0f;
+    td.maxMipmapLevelClamp = (float)(levels.size() - 1);
+    return cudaCreateTextureObject(tex, &rd, &td, nullptr);
+}
+cudaError_t make_weather_texture(const std::vector<uint8_t>& rgba, int w, int h, cudaArray_t* arr, cudaTextureObject_t* tex) {
+    cudaChannelFormatDesc fd = cudaCreateChannelDesc<uchar4>();
+    cudaError_t e = cudaMallocArray(arr, &fd, w, h, 0);
+    if (e != cudaSuccess) return e;
+    if ((e = cudaMemcpy2DToArray(*arr, 0, 0, rgba.data(), (size_t)w * 4, (size_t)w * 4, h, cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+    cudaResourceDesc rd = {};
+    rd.resType = cudaResourceTypeArray;
+    rd.res.array.array = *arr;
+    cudaTextureDesc td = {};
+    td.addressMode[0] = td.addressMode[1] = cudaAddressModeWrap;
+    td.filterMode = cudaFilterModeLinear;
+    td.readMode = cudaReadModeNormalizedFloat;
+    td.normalizedCoords = 1;
+    return cudaCreateTextureObject(tex, &rd, &td, nullptr);
 }
 
 bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
@@ -251,6 +305,9 @@ int upload_levels(cs_context* c, const std::vector<uint8_t>& large0, int ln, con
     }
     if (fmt & 4) { CU(put(&c->d_weather_f, wh16.data(), wh16.size() * 2)); }
     else { pack_weather_f(weather, ww, wh, pk); CU(put(&c->d_weather_f, pk.data(), pk.size() * 4)); }
+    CU(make_volume_texture(c->h_large, ln, &c->a_large, &c->t_large));
+    CU(make_volume_texture(c->h_small, sn, &c->a_small, &c->t_small));
+    CU(make_weather_texture(weather, ww, wh, &c->a_weather, &c->t_weather));
     c->have_tex = true;
     return CS_OK;
 }
@@ -284,6 +341,17 @@ int make_launch(cs_context* c, const cs_cloud_params* P, int x0, int y0, int x1,
     L.large_fn0 = (float)c->large_n * 0.00008f; L.small_fn0 = (float)c->small_n * 0.001f;
     L.weather_fw = (float)c->weather_w; L.weather_fh = (float)c->weather_h;
     L.large_mask0 = c->large_n - 1; L.small_mask0 = c->small_n - 1; L.weather_maskx = c->weather_w - 1; L.weather_masky = c->weather_h - 1;
+    // The 1^3 tail of the small volume's mip chain: any filtered fetch of it returns that texel's hfbm (clouds.glsl:133).
+    L.small_tail_level = -1;
+    if ((c->small_n >> (c->small_levels - 1)) == 1) {
+        const uint8_t* t = c->h_small[c->small_levels - 1].data();
+        L.small_tail_level = c->small_levels - 1;
+        if (c->mode & CS_MODE_TEX) L.small_tail_value = fmaf(un8(t[0]), 0.625f, fmaf(un8(t[1]), 0.25f, un8(t[2]) * 0.125f));
+        else if (c->records_half & 2) L.small_tail_value = (float)(5 * t[0] + 2 * t[1] + t[2]) * (1.0f / 2040.0f);
+        else L.small_tail_value = un8(t[0]) * 0.625f + un8(t[1]) * 0.25f + un8(t[2]) * 0.125f;
+    }
+    L.tex_large = c->t_large; L.tex_small = c->t_small; L.tex_weather = c->t_weather;
+    L.hw_filter = (c->mode & CS_MODE_TEX) ? 1 : 0;
     L.sky_lut = sky_lut ? sky_lut : c->d_sky;
     L.frame_consts = c->d_frame_consts;
     L.out = out;
@@ -555,8 +623,8 @@ int cs_resize(cs_context* c, int w, int h) {
 }
 int cs_set_march_config(cs_context* c, int p, int cone, int mode) {
     if (!c) return CS_ERR_INVALID;
-    if (p < 1 || p > 4096 || cone < 0 || cone > 64 || (mode != CS_MODE_FAST && mode != CS_MODE_STRICT && mode != (CS_MODE_FAST | CS_MODE_EARLY_OUT)))
-        return fail(c, CS_ERR_INVALID, "cs_set_march_config: primary_steps in [1,4096], cone_samples in [0,64], mode FAST | STRICT | FAST+EARLY_OUT");
+    if (p < 1 || p > 4096 || cone < 0 || cone > 64 || (mode != CS_MODE_STRICT && (mode & ~(CS_MODE_EARLY_OUT | CS_MODE_TEX)) != CS_MODE_FAST))
+        return fail(c, CS_ERR_INVALID, "cs_set_march_config: primary_steps in [1,4096], cone_samples in [0,64], mode STRICT, or FAST optionally | EARLY_OUT | TEX");
     c->primary_steps = p; c->cone_samples = cone; c->mode = mode;
     return CS_OK;
 }

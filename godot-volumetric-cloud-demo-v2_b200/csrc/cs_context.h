@@ -24,6 +24,10 @@ struct cs_context {
     float* d_large_f[cs::kMaxLargeLevels] = {};
     float* d_small_f[cs::kMaxSmallLevels] = {};
     float* d_weather_f = nullptr;
+    // CS_MODE_TEX: the same mip chains as CUDA mipmapped arrays behind texture objects
+    cudaMipmappedArray_t a_large = nullptr, a_small = nullptr;
+    cudaArray_t a_weather = nullptr;
+    cudaTextureObject_t t_large = 0, t_small = 0, t_weather = 0;
     std::vector<std::vector<uint8_t>> h_large, h_small;  // host copies of the mip chains (readback / repack)
 
     // LUTs

@@ -48,10 +48,15 @@ struct CloudLaunch {
     float large_fn0, small_fn0, weather_fw, weather_fh;   // level-0 texels per metre (edge * texture scale) and weather edges, used straight from the constant bank
     int large_mask0, small_mask0, weather_maskx, weather_masky;
     int records_half;     // format mask: bit 0 large_f, bit 1 small_f, bit 2 weather_f; set = fp16 records (32/16/16 B), clear = fp32 (64/32/32 B)
+    int small_tail_level;    // index of the 1^3 level of the small volume (-1: none)
+    float small_tail_value;  // its hfbm, computed the way the active sampler format would (context.cu)
     int weather_type_hi;  // 1 when every weather texel has R >= 128 (cloud type >= 0.5): affine height-gradient fast path
     const float* large_f[kMaxLargeLevels];  // 64 B per texel: 8 trilinear coefficients of R, then 8 of fbm
     const float* small_f[kMaxSmallLevels];  // 32 B per texel: 8 trilinear coefficients of hfbm
     const float* weather_f;                 // 32 B per texel: 4 bilinear coefficients of type, then 4 of coverage
+    // CS_MODE_TEX: texture objects over the same RGBA8 mip chains (REPEAT, linear, explicit level), filtered by the texture unit
+    unsigned long long tex_large, tex_small, tex_weather;  // cudaTextureObject_t
+    int hw_filter;                                          // 1: the fast kernel samples through the texture objects
     const uint16_t* sky_lut;                    // half4 200x100
     const float* frame_consts;                  // FrameConsts written by the prologue kernel
     uint16_t* out;                              // half4 image

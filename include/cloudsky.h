@@ -115,6 +115,12 @@ typedef struct cs_counters {
  * then already rounds to 1.0 in fp16 and the skipped radiance is below one fp16 ulp; executed (not nominal) primary steps
  * are reported by the counters.  Pays off for overcast skies (BASELINE config 5). */
 #define CS_MODE_EARLY_OUT 2
+/* Optional flag for CS_MODE_FAST (mode = CS_MODE_FAST | CS_MODE_TEX [| CS_MODE_EARLY_OUT]): sample the two noise volumes and
+ * the weather map through the GPU's texture unit (REPEAT, linear, explicit mip level) — what the reference's own sampler2D /
+ * sampler3D bindings do (cloud_sky.gd:389-398) — instead of the in-kernel fp32 trilinear filter.  The texture unit
+ * interpolates with 8-bit fixed-point weights, so results differ from the fp32-filtered oracle by up to ~3e-3 absolute
+ * (inside the FAST parity tolerance, tests/test_gpu_parity.py); texel values and mip chains are identical. */
+#define CS_MODE_TEX 4
 
 /* ---- lifetime -------------------------------------------------------------------------- */
 

@@ -4,6 +4,8 @@ Tolerances (stated here, justified in DESIGN.md §Parity):
   * LUTs (accurate kernels, --fmad=false):   |gpu - oracle| <= 1e-3 + 2e-3*|oracle|  on every texel
   * clouds STRICT (oracle operation order):  <= 1e-3 + 2e-3*|oracle| on >= 99.9 % of pixels
   * clouds FAST (FMA + MUFU intrinsics):     <= 2e-3 + 1e-2*|oracle| on >= 99.9 % of pixels
+  * clouds FAST | TEX (texture-unit filter): the same tolerance and pixel fraction as FAST (the texture unit's 8-bit
+    filter weights move a texel fetch by <= 1/512 of the local texel difference)
     (SURVEY 8(c)'s recommended criterion; an FMA-contracted build of the oracle itself only reaches
      99.91 % at this tolerance — the reference's fp32 arithmetic at 6e6 m is that ill-conditioned
      near the horizon; measured margins are in DESIGN.md section 5)
@@ -58,7 +60,7 @@ CASES = [
 
 
 @pytest.mark.parametrize("case", CASES)
-@pytest.mark.parametrize("mode", ["strict", "fast"])
+@pytest.mark.parametrize("mode", ["strict", "fast", "tex"])
 def test_clouds_match_oracle(cs, pair, helpers, oracle_lib, product_lib, case, mode):
     o, g, W, H = pair
     po = helpers.make_params(oracle_lib, W, H, **case)
@@ -69,7 +71,7 @@ def test_clouds_match_oracle(cs, pair, helpers, oracle_lib, product_lib, case, m
     o.build_sky_lut(sun)
     o.render_frame(po)
     ref = o.read_image()
-    g.set_march_config(128, 6, cs.MODE_STRICT if mode == "strict" else cs.MODE_FAST)
+    g.set_march_config(128, 6, {"strict": cs.MODE_STRICT, "fast": cs.MODE_FAST, "tex": cs.MODE_FAST | cs.MODE_TEX}[mode])
     g.write_sky_lut(o.read_sky_lut())  # identical LUT texels on both sides isolates the march
     g.render_frame(pg)
     out = g.read_image()
@@ -106,7 +108,8 @@ def test_all_cloud_types_and_small_volumes(cs, helpers, oracle_lib, product_lib)
         p = helpers.make_params(product_lib, W, H, **kw)
         o.render_frame(p)
         ref = o.read_image()
-        for mode, atol, rtol, need in ((cs.MODE_STRICT, 1e-3, 2e-3, 0.999), (cs.MODE_FAST, 2e-3, 1e-2, 0.999)):
+        for mode, atol, rtol, need in ((cs.MODE_STRICT, 1e-3, 2e-3, 0.999), (cs.MODE_FAST, 2e-3, 1e-2, 0.999),
+                                       (cs.MODE_FAST | cs.MODE_TEX, 2e-3, 1e-2, 0.999)):
             g.set_march_config(128, 6, mode)
             g.render_frame(p)
             out = g.read_image()
@@ -234,11 +237,11 @@ def test_counters_match_oracle(cs, pair, helpers, oracle_lib, product_lib):
     assert abs(kg["density_evals"] - ko["density_evals"]) <= 1e-3 * ko["density_evals"]
 
 
-@pytest.mark.parametrize("mode", ["strict", "fast"])
+@pytest.mark.parametrize("mode", ["strict", "fast", "tex"])
 def test_tile_invariance(cs, pair, helpers, product_lib, mode):
     """1, 4 and 64 tiles give bit-identical textures (cloud_sky.gd:156-161 tile walk)."""
     _, g, W, H = pair
-    g.set_march_config(128, 6, cs.MODE_STRICT if mode == "strict" else cs.MODE_FAST)
+    g.set_march_config(128, 6, {"strict": cs.MODE_STRICT, "fast": cs.MODE_FAST, "tex": cs.MODE_FAST | cs.MODE_TEX}[mode])
     g.build_sky_lut((0, 1, 0))
     p = helpers.make_params(product_lib, W, H, time=12.0)
     g.render_frame(p)
@@ -254,6 +257,40 @@ def test_tile_invariance(cs, pair, helpers, product_lib, mode):
                 g.dispatch_clouds(q, (tw + 7) // 8, (th + 7) // 8)
         tiled = g.read_image()
         assert (tiled.view(np.uint16) == full.view(np.uint16)).all()
+    g.set_march_config(128, 6, cs.MODE_FAST)
+
+
+def test_texture_unit_mode(cs, pair, helpers, oracle_lib, product_lib):
+    """CS_MODE_FAST | CS_MODE_TEX (opt-in): the texture unit filters the noise volumes and the weather map, as the
+    reference's sampler bindings do (cloud_sky.gd:389-398), with 8-bit fixed-point filter weights instead of the oracle's
+    fp32 ones.  It stays close to the in-kernel-filter FAST image, composes with the early-out flag, handles non-reference
+    march shapes (sequential fallback beyond 16 light samples) and is rejected together with STRICT."""
+    o, g, W, H = pair
+    p = helpers.make_params(product_lib, W, H, time=3.0)
+    o.set_march_config(128, 6); o.build_sky_lut(tuple(p.light_direction)); o.render_frame(p)
+    ref = o.read_image()
+    g.write_sky_lut(o.read_sky_lut())
+    g.set_march_config(128, 6, cs.MODE_FAST); g.render_frame(p)
+    fast = g.read_image()
+    g.set_march_config(128, 6, cs.MODE_FAST | cs.MODE_TEX); g.render_frame(p)
+    tex = g.read_image()
+    assert not (tex.view(np.uint16) == fast.view(np.uint16)).all()      # it really is a different sampler
+    frac, mx = helpers.compare_images(tex, fast, 2e-3, 1e-2)
+    assert frac >= 0.9995 and mx < 0.02, (frac, mx)
+    g.set_march_config(128, 6, cs.MODE_FAST | cs.MODE_TEX | cs.MODE_EARLY_OUT); g.render_frame(p)
+    early = g.read_image()
+    assert (early[..., 3].view(np.uint16) == tex[..., 3].view(np.uint16)).all()
+    d = np.abs(early[..., :3].view(np.int16).astype(np.int32) - tex[..., :3].view(np.int16).astype(np.int32))
+    assert d.max() <= 2, d.max()
+    for P, cone in ((64, 3), (128, 20)):  # 20 cone samples: more than the cooperative tables hold -> sequential light walk
+        o.set_march_config(P, cone); o.render_frame(p)
+        g.set_march_config(P, cone, cs.MODE_FAST | cs.MODE_TEX); g.render_frame(p)
+        frac, mx = helpers.compare_images(g.read_image(), o.read_image(), 2e-3, 1e-2)
+        assert frac >= 0.998, (P, cone, frac, mx)
+    with pytest.raises(cs.CloudSkyError):
+        g.set_march_config(128, 6, cs.MODE_STRICT | cs.MODE_TEX)
+    o.set_march_config(128, 6)
+    g.set_march_config(128, 6, cs.MODE_FAST)
 
 
 def test_generalised_step_counts(cs, pair, helpers, oracle_lib, product_lib):

@@ -13,6 +13,7 @@ def main():
     cfgs = [(2048, 1024, 128, 6, 0.2), (2048, 1024, 128, 7, 0.2), (2048, 1024, 128, 7, 1.0), (1024, 512, 64, 5, 0.2)]
     if "--only" in sys.argv:
         cfgs = [cfgs[int(sys.argv[sys.argv.index("--only") + 1])]]
+    flags = int(sys.argv[sys.argv.index("--flags") + 1]) if "--flags" in sys.argv else 0  # MODE_EARLY_OUT (2) | MODE_TEX (4)
     for (W, H, P, cone, cov) in cfgs:
         ctx = lib.context(0)
         ctx.upload_textures(large, small, weather)
@@ -21,7 +22,7 @@ def main():
         st = lib.frame_state_init(); st.light_direction[:] = [0, 1, 0]
         lib.frame_advance(st, s, 1.0)
         p = lib.fill_cloud_params(s, st, W, H)
-        for mode, name in ((cs.MODE_FAST, "fast"), (cs.MODE_STRICT, "strict")):
+        for mode, name in ((cs.MODE_FAST | flags, "fast" + (f"+{flags}" if flags else "")), (cs.MODE_STRICT, "strict")):
             if name == "strict" and "--strict" not in sys.argv and (cone != 6):
                 continue
             ctx.set_march_config(P, cone, mode)
