@@ -200,10 +200,10 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic():
+def ncu_traffic(name="roofline_latest.json"):
     """dram bytes per launch of the march kernel from the committed `ncu --set full` capture, if any."""
     try:
-        with open(os.path.join(ROOT, "profiles", "roofline_latest.json")) as f:
+        with open(os.path.join(ROOT, "profiles", name)) as f:
             d = json.load(f)
         return d.get("dram_bytes_per_launch"), d.get("source"), {k: d.get(k) for k in ("l2_hit_pct", "l1_hit_pct", "issue_active_pct")}
     except Exception:
@@ -237,7 +237,8 @@ def run_ours(args):
     ctx.upload_textures(large, small, weather)
     ctx.build_transmittance_lut()
     ctx.resize(W, H)
-    ctx.set_march_config(PRIMARY, CONE, cs.MODE_FAST)
+    base_mode = cs.MODE_FAST | (cs.MODE_TEX if args.sampler == "texture" else 0)
+    ctx.set_march_config(PRIMARY, CONE, base_mode)
     sun = sun_for_rank(rank, world)
     # two gathered buffers: the all-gather of step k (on a side stream) overlaps the kernels of step k+1
     gathered = [torch.zeros((world, H, W, 4), dtype=torch.float16, device="cuda") for _ in range(2 if world > 1 else 1)]
@@ -350,7 +351,7 @@ def run_ours(args):
     # SURVEY 7.3-5 asks for nominal AND executed steps to be reported).  Measured after the timed region.
     early = None
     if world == 1:
-        ctx.set_march_config(PRIMARY, CONE, cs.MODE_FAST | cs.MODE_EARLY_OUT)
+        ctx.set_march_config(PRIMARY, CONE, base_mode | cs.MODE_EARLY_OUT)
         ctx.set_counters_enabled(True)
         ctx.render_frame(params[0])
         k_early = ctx.get_counters().as_dict()
@@ -360,7 +361,17 @@ def run_ours(args):
                  "value_on_executed_steps": round(k_early["primary_steps"] / ms_early / 1e3, 1),
                  "executed_step_fraction": round(k_early["primary_steps"] / (counters["marched_pixels"] * PRIMARY), 4),
                  "note": "opt-in mode flag, not reference behaviour (clouds.glsl:172 runs every step); not used for value / e2e"}
-        ctx.set_march_config(PRIMARY, CONE, cs.MODE_FAST)
+        ctx.set_march_config(PRIMARY, CONE, base_mode)
+
+    # Extra, NOT the headline: the opt-in CS_MODE_TEX flag (the texture unit filters the three input textures with its 8-bit
+    # fixed-point weights, like the reference's own sampler bindings; the headline keeps the in-kernel fp32 filter).
+    tex_extra = None
+    if world == 1 and args.sampler == "kernel":
+        ctx.set_march_config(PRIMARY, CONE, cs.MODE_FAST | cs.MODE_TEX)
+        ms_tex = ctx.time_render_frame(params[0], 3, 10)
+        tex_extra = {"march_ms": round(ms_tex, 4), "value_march_only": round(ray_steps_per_frame / ms_tex / 1e3, 1),
+                     "note": "opt-in mode flag (bench.py --sampler texture runs the whole bench in it); same parity tolerance as FAST, tests/test_gpu_parity.py"}
+        ctx.set_march_config(PRIMARY, CONE, base_mode)
 
     if rank != 0:
         if dist is not None:
@@ -371,7 +382,7 @@ def run_ours(args):
     alg_bytes = 80 * counters["density_evals"] + 8 * W * H  # 80 B per density evaluation + 8 B per pixel
     march_ms = kt["march_ms"] / max(1, kt["march_launches"])
     achieved = alg_bytes / (march_ms * 1e-3) / 1e9
-    traffic, traffic_src, ncu_extra = ncu_traffic()
+    traffic, traffic_src, ncu_extra = ncu_traffic("roofline_tex.json" if args.sampler == "texture" else "roofline_latest.json")
     roofline = {"bound": "hbm", "kernel": "clouds_fast_kernel", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "kernel_ms": round(march_ms, 4), "algorithmic_bytes_per_launch": alg_bytes, "ncu": ncu_extra,
@@ -383,6 +394,7 @@ def run_ours(args):
             "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": desc,
             "config": {"workload": WORKLOAD, "width": W, "height": H, "primary_steps": PRIMARY, "light_steps": LIGHT, "cone_samples": CONE,
+                       "sampler": "in-kernel fp32 trilinear (coefficient records)" if args.sampler == "kernel" else "texture unit (CS_MODE_TEX, 8-bit filter weights)",
                        "l2": f"flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB memset outside the per-step event pairs)",
                        "parallelism": "1 GPU" if world == 1 else f"{world} GPUs: one sun-angle frame per rank + one NCCL all-gather of the finished textures per step (side stream, overlaps the next step)",
                        "lit_fraction": round(counters["lit_steps"] / counters["primary_steps"], 4),
@@ -391,7 +403,7 @@ def run_ours(args):
             "kernels": {"march_ms_avg": round(march_ms, 4), "sky_lut_ms_avg": round(kt["sky_ms"] / max(1, kt["sky_launches"]), 4)},
             "gevals_per_s": round(world * counters["density_evals"] * args.steps / (dev_ms * 1e-3) / 1e9, 2),
             "wall_ms_per_step_incl_flush": round(1e3 * t_wall / args.steps, 3), "clocks": clocks,
-            "early_out_mode": early,
+            "early_out_mode": early, "texture_unit_mode": tex_extra,
             "per_rank_kernel_ms": per_rank_kernel_ms,  # sky LUT + march per step on every rank (load balance)
             "value_without_gather": round(world * ray_steps_per_frame / (max(per_rank_kernel_ms) * 1e-3) / 1e6, 1)}
     if cpu_v is not None:
@@ -408,6 +420,8 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--sampler", default="kernel", choices=["kernel", "texture"],
+                    help="kernel: in-kernel fp32 trilinear filter (default, the headline); texture: CS_MODE_TEX, the GPU texture unit filters")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

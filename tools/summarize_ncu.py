@@ -29,6 +29,7 @@ UNIT = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
 
 def main():
     rep, out, cmd = sys.argv[1], sys.argv[2], (sys.argv[3] if len(sys.argv) > 3 else "")
+    roofline_out = sys.argv[4] if len(sys.argv) > 4 else None  # e.g. profiles/roofline_latest.json; not written unless named
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
@@ -43,12 +44,12 @@ def main():
         kernels.append({"kernel": d.get("Kernel Name"), "dram_bytes": dram, "metrics": m})
     summary = {"report": rep, "command": cmd, "launches": kernels}
     json.dump(summary, open(out, "w"), indent=1)
-    if kernels:
+    if kernels and roofline_out:
         k = kernels[-1]
         hit = lambda name: float(k["metrics"][name]["value"]) if name in k["metrics"] else None
         json.dump({"dram_bytes_per_launch": k["dram_bytes"], "kernel": k["kernel"], "l2_hit_pct": hit("lts__t_sector_hit_rate.pct"),
                    "l1_hit_pct": hit("l1tex__t_sector_hit_rate.pct"), "issue_active_pct": hit("smsp__issue_active.avg.pct_of_peak_sustained_active"), "source": f"{out} (ncu --set full --clock-control none: dram__bytes_read.sum + dram__bytes_write.sum)"},
-                  open("profiles/roofline_latest.json", "w"), indent=1)
+                  open(roofline_out, "w"), indent=1)
     print(json.dumps({k["kernel"]: k["dram_bytes"] for k in kernels}))
 
 
