@@ -111,6 +111,17 @@ class Counters(C.Structure):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}
 
 
+class NoiseParams(C.Structure):
+    """cs_noise_params: knobs of the noise generator (README.md:30 TODO)."""
+    _fields_ = [
+        ("seed", C.c_uint32), ("worley_frequency", C.c_int32), ("worley_scale", C.c_float), ("perlin_frequency", C.c_int32), ("perlin_octaves", C.c_int32),
+        ("perlin_scale", C.c_float), ("remap_lo", C.c_float), ("remap_hi", C.c_float), ("type_lo", C.c_float), ("type_hi", C.c_float),
+    ]
+
+
+NOISE_LARGE, NOISE_SMALL, NOISE_WEATHER = 0, 1, 2
+
+
 class View(C.Structure):
     """cs_view: which directions the presentation composite shades (clouds.gdshader EYEDIR)."""
     _fields_ = [
@@ -166,6 +177,8 @@ _PROTOTYPES = {
     "cs_decode_image_file": (C.c_int, [C.c_char_p, C.POINTER(_P), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "cs_free": (None, [_P]),
     "cs_read_volume_level": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_size_t]),
+    "cs_noise_params_default": (None, [C.c_int, C.POINTER(NoiseParams)]),
+    "cs_generate_noise": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(NoiseParams), _P, C.c_size_t]),
     "cs_build_transmittance_lut": (C.c_int, [_P]),
     "cs_build_sky_lut": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "cs_read_transmittance_lut": (C.c_int, [_P, _P, C.c_size_t]),
@@ -244,6 +257,11 @@ class Library:
         s = SkySettings()
         self.dll.cs_settings_demo(C.byref(s))
         return s
+
+    def noise_params_default(self, kind: int) -> NoiseParams:
+        p = NoiseParams()
+        self.dll.cs_noise_params_default(kind, C.byref(p))
+        return p
 
     def frame_state_init(self) -> FrameState:
         st = FrameState()
@@ -350,6 +368,13 @@ class Context:
         n = n0 >> level
         out = np.empty((n, n, n, 4), np.uint8)
         self._ck(self.lib.dll.cs_read_volume_level(self._h, which, level, out.ctypes.data, out.nbytes))
+        return out
+
+    def generate_noise(self, kind: int, n: int, params: "NoiseParams | None" = None) -> np.ndarray:
+        """cs_generate_noise: RGBA8 [n,n,n,4] (z,y,x order, as upload_textures takes it) or [n,n,4] for the weather map."""
+        p = params if params is not None else self.lib.noise_params_default(kind)
+        out = np.empty((n, n, 4) if kind == NOISE_WEATHER else (n, n, n, 4), np.uint8)
+        self._ck(self.lib.dll.cs_generate_noise(self._h, kind, n, C.byref(p), out.ctypes.data, out.nbytes))
         return out
 
     # LUTs ---------------------------------------------------------------------------------

@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "cs_context.h"
+#include "noise_core.h"
 
 using namespace cs;
 
@@ -544,6 +545,24 @@ int cs_read_volume_level(cs_context* c, int which, int level, uint8_t* out, size
     int r = bind(c);
     if (r) return r;
     CU(cudaMemcpy(out, d, bytes, cudaMemcpyDeviceToHost));  // read back what the kernels actually sample
+    return CS_OK;
+}
+
+int cs_generate_noise(cs_context* c, int kind, int n, const cs_noise_params* P, uint8_t* out, size_t bytes) {
+    if (!c) return CS_ERR_INVALID;
+    if (const char* why = nz::check_request(kind, n, P)) return fail(c, CS_ERR_INVALID, why);
+    const size_t texels = kind == CS_NOISE_WEATHER ? (size_t)n * n : (size_t)n * n * n;
+    if (!out || bytes != texels * 4) return fail(c, CS_ERR_INVALID, "cs_generate_noise: out_bytes must be texels * 4");
+    int r = bind(c);
+    if (r) return r;
+    uint32_t* d = nullptr;
+    CU(cudaMalloc(&d, bytes));
+    launch_noise(kind, n, *P, d, c->stream);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d, bytes, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return cuda_fail(c, e, "cs_generate_noise");
     return CS_OK;
 }
 

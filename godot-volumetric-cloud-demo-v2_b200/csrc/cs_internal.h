@@ -80,5 +80,6 @@ void launch_sky_lut(const uint16_t* transmittance_half4, const float sun_dir[3],
 void launch_clouds_prologue(const CloudLaunch& L, bool strict, void* stream);
 void launch_clouds_strict(const CloudLaunch& L, void* stream);
 void launch_clouds_fast(const CloudLaunch& L, void* stream);
+void launch_noise(int kind, int n, const cs_noise_params& P, uint32_t* out_rgba8, void* stream);  // noise_gen.cu
 
 }  // namespace cs

@@ -7,6 +7,20 @@
 
 extern "C" {
 
+// Generator defaults (cs_generate_noise; README.md:30 TODO).  Chosen so that the products have the rough statistics of the
+// reference bitmaps (perlworlnoise R mean ~0.85, weather type 0.59..0.91, coverage spanning 0..1).
+void cs_noise_params_default(int kind, cs_noise_params* p) {
+    if (!p) return;
+    p->seed = 1u;
+    p->worley_frequency = kind == CS_NOISE_SMALL ? 2 : 4;
+    p->worley_scale = kind == CS_NOISE_WEATHER ? 1.0f : 0.56f;
+    p->perlin_frequency = 4;
+    p->perlin_octaves = kind == CS_NOISE_WEATHER ? 4 : 5;
+    p->perlin_scale = 1.0f;
+    p->remap_lo = 0.55f; p->remap_hi = 0.95f;
+    p->type_lo = 0.59f; p->type_hi = 0.91f;
+}
+
 // Exported property defaults (cloud_sky.gd:9-50).
 void cs_settings_default(cs_sky_settings* s) {
     if (!s) return;

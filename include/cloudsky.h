@@ -167,6 +167,31 @@ void cs_free(void* p);
  * (level 0 = the upload).  out must hold (n>>level)^3*4 bytes. */
 int cs_read_volume_level(cs_context* ctx, int which, int level, uint8_t* out, size_t out_bytes);
 
+/* ---- noise synthesis (README.md:30 TODO "Implement a noise generator so custom noise can be created and tweaked"; ----
+ * ---- SURVEY 8(f)-3): tileable stand-ins for the three bitmap inputs, at any power-of-two resolution --------------- */
+
+#define CS_NOISE_LARGE 0   /* n^3 RGBA8: R Perlin-Worley, G/B/A Worley fBm at rising frequencies (perlworlnoise.tga; clouds.glsl:117-119) */
+#define CS_NOISE_SMALL 1   /* n^3 RGBA8: R/G/B Worley fBm at rising frequencies, A = 255 (worlnoise.bmp; clouds.glsl:132-133)            */
+#define CS_NOISE_WEATHER 2 /* n^2 RGBA8: R cloud type, G = 0, B coverage, A = 255 (weather.bmp; clouds.glsl:121,123)                      */
+typedef struct cs_noise_params {
+    uint32_t seed;
+    int32_t worley_frequency; /* feature cells across the tile of the lowest Worley octave (octave k uses frequency << k) */
+    float worley_scale;       /* Worley value = 1 - min(worley_scale * distance to the nearest feature point in cells, 1) */
+    int32_t perlin_frequency; /* lattice cells across the tile of the first Perlin octave                               */
+    int32_t perlin_octaves;   /* 1..8                                                                                   */
+    float perlin_scale;       /* perlin01 = clamp(0.5 + perlin_scale * fBm)                                             */
+    float remap_lo, remap_hi; /* weather coverage = clamp((perlin-worley - remap_lo) / (remap_hi - remap_lo))           */
+    float type_lo, type_hi;   /* weather cloud type range (the reference map spans 0.59..0.91)                          */
+} cs_noise_params;
+/* Defaults per kind (large: Worley 4 / Perlin 4 x 5 octaves; small: Worley 2; weather: Worley 4 / Perlin 4 x 4 octaves,
+ * coverage remap 0.55..0.95, type 0.59..0.91; worley_scale 0.56 puts the Worley channels' mean near the 0.71 of the
+ * reference bitmaps). */
+void cs_noise_params_default(int kind, cs_noise_params* out);
+/* Generate one texture on the device and copy it to out_rgba8 (host; n^3*4 bytes for the volumes, x fastest then y then z
+ * as cs_upload_textures expects with 4 channels; n*n*4 for the weather map).  n: power of two.  Every backend produces the
+ * same bytes (integer lattice hash, fp32 + - * / sqrt only, fixed evaluation order). */
+int cs_generate_noise(cs_context* ctx, int kind, int n, const cs_noise_params* params, uint8_t* out_rgba8, size_t out_bytes);
+
 /* ---- atmosphere LUTs -------------------------------------------------------------------- */
 
 /* Replaces transmittance_lut.gd:_initialize_compute_code's one dispatch (32x8 groups,

@@ -406,6 +406,9 @@ struct CloudCtx {
     const Volume* large; const Volume* small; const Image8* weather; const uint16_t* sky_lut;
     cs_cloud_params P;
     int primary_steps, cone_samples;
+    int hier_stride = 0;        // > 1: hierarchical-march STUDY (README.md:28 TODO, not reference behaviour; cso_set_hierarchical)
+    float hier_margin = 0.0f;
+    int hier_lod_bias = 0;
 };
 struct Tally { uint64_t px = 0, steps = 0, lit = 0, evals = 0; };
 
@@ -487,6 +490,23 @@ float density(const CloudCtx& c, V3 pip, V3 weather, float mip, Tally& tl) {
     return powf(clampf(base_cloud, 0.0f, 1.0f), (1.0f - height_fraction) * 0.8f + 0.5f);
 }
 
+// Probe of the hierarchical-march study (cso_set_hierarchical): density() of clouds.glsl:109-126 up to the coverage
+// remap, i.e. WITHOUT the detail erosion of :127-136 (which only ever lowers the value), before the `* weather_coverage`
+// (positive factor) — the sign of `base_cloud * g - (1 - weather_coverage)` is the sign of that remap.
+float density_probe(const CloudCtx& c, V3 pip, V3 weather, float lod, Tally& tl) {
+    tl.evals++;
+    V3 p = pip;
+    float height_fraction = GetHeightFractionForPoint(length3(p));
+    p.x += 20.0f * c.P.cloud_pos[0] * 0.6f;
+    p.z += 20.0f * c.P.cloud_pos[1] * 0.6f;
+    V4 n = sample_volume(*c.large, {p.x * 0.00008f, p.y * 0.00008f, p.z * 0.00008f}, lod);
+    float fbm = n.y * 0.625f + n.z * 0.25f + n.w * 0.125f;
+    float g = densityHeightGradient(height_fraction, weather.x);
+    float base_cloud = remap(n.x, -(1.0f - fbm), 1.0f, 0.0f, 1.0f);
+    float weather_coverage = c.P.cloud_coverage * weather.z;
+    return base_cloud * g - (1.0f - weather_coverage);
+}
+
 const V3 RANDOM_VECTORS[6] = {  // clouds.glsl:140
     {0.38051305f, 0.92453449f, -0.02111345f}, {-0.50625799f, -0.03590792f, -0.86163418f},
     {-0.32509218f, -0.94557439f, 0.01428793f}, {0.09026238f, -0.27376545f, 0.95755165f},
@@ -526,7 +546,25 @@ V4 march(const CloudCtx& c, V3 pos, V3 /*end*/, V3 dir, int depth, Tally& tl) {
     V2 weather_pos = {P.weather_pos[0], P.weather_pos[1]};
     const int max_small_mip = 5;
 
+    // Hierarchical-march study (off unless cso_set_hierarchical was called): the primary steps are grouped into blocks of hier_stride; one probe at the centre of a block's
+    // sample positions (large volume only, at the mip level whose texel matches the block length) decides whether the
+    // block is marched at all.  The ray positions are the reference's own (p advances by the same fp32 adds).
+    const int S = c.hier_stride > 1 ? c.hier_stride : 0;
+    float probe_lod = 0.0f;
+    if (S) {
+        float texel = 1.0f / ((float)c.large->n * 0.00008f);
+        int l = (int)floorf(log2f(fmaxf((float)S * ss / texel, 1.0f))) + c.hier_lod_bias;
+        probe_lod = (float)std::min(std::max(l, 0), c.large->levels - 1);
+    }
+    int skip = 0;
     for (int i = 0; i < depth; i++) {
+        if (S && i % S == 0) {
+            int nb = std::min(S, depth - i);
+            V3 q = p + dir * (ss * (0.5f * (float)(nb + 1)));
+            V3 wq = sample_weather(*c.weather, {q.x * weather_scale + 0.5f + weather_pos.x, q.z * weather_scale + 0.5f + weather_pos.y});
+            skip = density_probe(c, q, wq, probe_lod, tl) > -c.hier_margin ? 0 : nb;
+        }
+        if (skip > 0) { skip--; p = p + dir * ss; continue; }
         tl.steps++;
         p = p + dir * ss;
         V3 weather_sample = sample_weather(*c.weather, {p.x * weather_scale + 0.5f + weather_pos.x, p.z * weather_scale + 0.5f + weather_pos.y});
@@ -629,6 +667,8 @@ struct cs_context {
     int W = 0, H = 0;
     std::vector<uint16_t> image;
     int primary_steps = CS_REF_PRIMARY_STEPS, cone_samples = CS_REF_CONE_SAMPLES;
+    int hier_stride = 0, hier_lod_bias = 0;
+    float hier_margin = 0.0f;
     cs_counters counters{};
 };
 
@@ -737,6 +777,7 @@ static int render_region(cs_context* c, const cs_cloud_params* P, int x0, int y0
     if ((int)P->texture_size[0] != c->W || (int)P->texture_size[1] != c->H) return fail(c, CS_ERR_INVALID, "params.texture_size != image size");
     x0 = std::max(x0, 0); y0 = std::max(y0, 0); x1 = std::min(x1, c->W); y1 = std::min(y1, c->H);
     CloudCtx cc{&c->large, &c->small, &c->weather, c->skylut.data(), *P, c->primary_steps, c->cone_samples};
+    cc.hier_stride = c->hier_stride; cc.hier_margin = c->hier_margin; cc.hier_lod_bias = c->hier_lod_bias;
     std::vector<Tally> tl((size_t)std::max(c->threads, 1));
     parallel_rows(c->threads, std::max(y1 - y0, 0), [&](int r, int t) {
         int y = y0 + r;
@@ -794,6 +835,131 @@ int cs_time_render_frame(cs_context* c, const cs_cloud_params*, int, int, float*
 
 int cs_set_kernel_timing(cs_context* c, int) { return fail(c, CS_ERR_UNSUPPORTED, "device timing is CUDA-only"); }
 int cs_read_kernel_timings(cs_context* c, float*, int*, float*, int*) { return fail(c, CS_ERR_UNSUPPORTED, "device timing is CUDA-only"); }
+
+// ---- noise synthesis (cs_generate_noise; README.md:30 TODO) ----------------------------------------
+// CPU statement of the generator defined in include/cloudsky.h: integer lattice hash, inverted Worley F1 with one
+// feature point per cell, hash-gradient Perlin noise with quintic fade, fBm 1/2,1/4,..., the shader's own 0.625/0.25/0.125
+// channel weights (clouds.glsl:118,133).  The reference has no generator to follow (its noise ships as bitmaps), so this
+// is the definition the CUDA kernel is checked against, byte for byte.
+} // extern "C"
+namespace noisegen {
+uint32_t finalise(uint32_t h) { h ^= h >> 16; h *= 0x7feb352du; h ^= h >> 15; h *= 0x846ca68bu; h ^= h >> 16; return h; }
+uint32_t hash_cell(int x, int y, int z, uint32_t seed) {
+    uint32_t h = finalise(seed);
+    h = finalise((uint32_t)z + h);
+    h = finalise((uint32_t)y + h);
+    return finalise((uint32_t)x + h);
+}
+float to_unit(uint32_t h) { return (float)(h >> 8) / 16777216.0f; }
+int modp(int i, int f) { int m = i % f; return m < 0 ? m + f : m; }
+
+float worley_inv(const float p[3], int freq, float scale, uint32_t seed) {
+    float q[3], fr[3]; int cell[3];
+    for (int a = 0; a < 3; a++) { q[a] = p[a] * (float)freq; float fl = floorf(q[a]); fr[a] = q[a] - fl; cell[a] = (int)fl; }
+    float nearest2 = 1.0e30f;
+    for (int k = 0; k < 27; k++) {  // dx fastest, then dy, then dz
+        int d[3] = {k % 3 - 1, (k / 3) % 3 - 1, k / 9 - 1};
+        uint32_t hx = hash_cell(modp(cell[0] + d[0], freq), modp(cell[1] + d[1], freq), modp(cell[2] + d[2], freq), seed);
+        uint32_t hy = finalise(hx + 0x9e3779b9u);
+        uint32_t hz = finalise(hy + 0x9e3779b9u);
+        uint32_t hh[3] = {hx, hy, hz};
+        float r[3];
+        for (int a = 0; a < 3; a++) r[a] = ((float)d[a] + to_unit(hh[a])) - fr[a];
+        float d2 = (r[0] * r[0] + r[1] * r[1]) + r[2] * r[2];
+        if (d2 < nearest2) nearest2 = d2;
+    }
+    float dist = sqrtf(nearest2) * scale;
+    return 1.0f - (dist < 1.0f ? dist : 1.0f);
+}
+float corner_gradient(uint32_t h, float x, float y, float z) {
+    static const int gx[16] = {1, -1, 1, -1, 1, -1, 1, -1, 0, 0, 0, 0, 1, 0, -1, 0};
+    static const int gy[16] = {1, 1, -1, -1, 0, 0, 0, 0, 1, -1, 1, -1, 1, -1, 1, -1};
+    static const int gz[16] = {0, 0, 0, 0, 1, 1, -1, -1, 1, 1, -1, -1, 0, 1, 0, -1};
+    // the 12 edge directions (+4 repeats), written as the sum of the two non-zero signed components in (first, second) order
+    int i = (int)(h & 15u);
+    float first, second;
+    if (gx[i] != 0 && gy[i] != 0) { first = gx[i] > 0 ? x : -x; second = gy[i] > 0 ? y : -y; }
+    else if (gx[i] != 0) { first = gx[i] > 0 ? x : -x; second = gz[i] > 0 ? z : -z; }
+    else { first = gy[i] > 0 ? y : -y; second = gz[i] > 0 ? z : -z; }
+    return first + second;
+}
+float quintic(float t) { return t * t * t * (t * (t * 6.0f - 15.0f) + 10.0f); }
+float gradient_noise(const float p[3], int freq, uint32_t seed) {
+    float t[3]; int lo[3], hi[3];
+    for (int a = 0; a < 3; a++) { float q = p[a] * (float)freq; float fl = floorf(q); t[a] = q - fl; lo[a] = (int)fl; hi[a] = modp(lo[a] + 1, freq); }
+    float corner[2][2][2];
+    for (int cz = 0; cz < 2; cz++)
+        for (int cy = 0; cy < 2; cy++)
+            for (int cx = 0; cx < 2; cx++)
+                corner[cz][cy][cx] = corner_gradient(hash_cell(cx ? hi[0] : lo[0], cy ? hi[1] : lo[1], cz ? hi[2] : lo[2], seed),
+                                                     cx ? t[0] - 1.0f : t[0], cy ? t[1] - 1.0f : t[1], cz ? t[2] - 1.0f : t[2]);
+    float u = quintic(t[0]), v = quintic(t[1]), w = quintic(t[2]);
+    float plane[2];
+    for (int cz = 0; cz < 2; cz++) {
+        float e0 = lerpf(corner[cz][0][0], corner[cz][0][1], u), e1 = lerpf(corner[cz][1][0], corner[cz][1][1], u);
+        plane[cz] = lerpf(e0, e1, v);
+    }
+    return lerpf(plane[0], plane[1], w);
+}
+float gradient_fbm(const float p[3], int freq, int octaves, uint32_t seed) {
+    float total = 0.0f, amplitude = 0.5f;
+    for (int o = 0; o < octaves; o++) { total = total + amplitude * gradient_noise(p, freq << o, seed + (uint32_t)o); amplitude = amplitude * 0.5f; }
+    return total;
+}
+float sat01(float x) { return clampf(x, 0.0f, 1.0f); }
+uint8_t quantise(float v) { return (uint8_t)(int)(sat01(v) * 255.0f + 0.5f); }
+float weights3(float a, float b, float c) { return (a * 0.625f + b * 0.25f) + c * 0.125f; }
+
+void texel(int kind, const cs_noise_params& P, int n, int x, int y, int z, uint8_t* out) {
+    float p[3] = {((float)x + 0.5f) * (1.0f / (float)n), ((float)y + 0.5f) * (1.0f / (float)n), kind == CS_NOISE_WEATHER ? 0.0f : ((float)z + 0.5f) * (1.0f / (float)n)};
+    if (kind == CS_NOISE_WEATHER) {
+        float wf = weights3(worley_inv(p, P.worley_frequency, P.worley_scale, P.seed), worley_inv(p, P.worley_frequency * 2, P.worley_scale, P.seed + 101u),
+                            worley_inv(p, P.worley_frequency * 4, P.worley_scale, P.seed + 202u));
+        float p01 = sat01(0.5f + P.perlin_scale * gradient_fbm(p, P.perlin_frequency, P.perlin_octaves, P.seed ^ 0x5bd1e995u));
+        float pw = wf + p01 * (1.0f - wf);
+        float t01 = sat01(0.5f + P.perlin_scale * gradient_fbm(p, 2, 3, P.seed ^ 0x2545f491u));
+        out[0] = quantise(P.type_lo + (P.type_hi - P.type_lo) * t01);
+        out[1] = 0;
+        out[2] = quantise(sat01((pw - P.remap_lo) / (P.remap_hi - P.remap_lo)));
+        out[3] = 255;
+        return;
+    }
+    float oct[5];
+    for (int k = 0; k < 5; k++) oct[k] = worley_inv(p, P.worley_frequency << k, P.worley_scale, P.seed + 101u * (uint32_t)k);
+    float f0 = weights3(oct[0], oct[1], oct[2]), f1 = weights3(oct[1], oct[2], oct[3]), f2 = weights3(oct[2], oct[3], oct[4]);
+    if (kind == CS_NOISE_SMALL) { out[0] = quantise(f0); out[1] = quantise(f1); out[2] = quantise(f2); out[3] = 255; return; }
+    float p01 = sat01(0.5f + P.perlin_scale * gradient_fbm(p, P.perlin_frequency, P.perlin_octaves, P.seed ^ 0x5bd1e995u));
+    out[0] = quantise(f0 + p01 * (1.0f - f0));
+    out[1] = quantise(f0); out[2] = quantise(f1); out[3] = quantise(f2);
+}
+}  // namespace noisegen
+extern "C" {
+void cs_noise_params_default(int kind, cs_noise_params* p) {
+    if (!p) return;
+    p->seed = 1u;
+    p->worley_frequency = kind == CS_NOISE_SMALL ? 2 : 4;
+    p->worley_scale = kind == CS_NOISE_WEATHER ? 1.0f : 0.56f;
+    p->perlin_frequency = 4;
+    p->perlin_octaves = kind == CS_NOISE_WEATHER ? 4 : 5;
+    p->perlin_scale = 1.0f;
+    p->remap_lo = 0.55f; p->remap_hi = 0.95f;
+    p->type_lo = 0.59f; p->type_hi = 0.91f;
+}
+int cs_generate_noise(cs_context* c, int kind, int n, const cs_noise_params* P, uint8_t* out, size_t bytes) {
+    if (!c) return CS_ERR_INVALID;
+    if (kind < CS_NOISE_LARGE || kind > CS_NOISE_WEATHER || !P) return fail(c, CS_ERR_INVALID, "cs_generate_noise: bad kind / params");
+    if (n < 1 || n > (kind == CS_NOISE_WEATHER ? 8192 : 512) || (n & (n - 1))) return fail(c, CS_ERR_INVALID, "cs_generate_noise: n must be a power of two");
+    if (P->worley_frequency < 1 || P->worley_frequency > 256 || P->perlin_frequency < 1 || P->perlin_frequency > 256 || P->perlin_octaves < 1 || P->perlin_octaves > 8 ||
+        !(P->remap_hi > P->remap_lo) || !(P->type_hi >= P->type_lo) || !(P->perlin_scale >= 0.0f) || !(P->worley_scale > 0.0f))
+        return fail(c, CS_ERR_INVALID, "cs_generate_noise: bad parameters");
+    const int depth = kind == CS_NOISE_WEATHER ? 1 : n;
+    if (!out || bytes != (size_t)n * n * depth * 4) return fail(c, CS_ERR_INVALID, "cs_generate_noise: out_bytes must be texels * 4");
+    parallel_rows(c->threads, n * depth, [&](int row, int) {
+        int y = row % n, z = row / n;
+        for (int x = 0; x < n; x++) noisegen::texel(kind, *P, n, x, y, z, out + (((size_t)z * n + y) * n + x) * 4);
+    });
+    return CS_OK;
+}
 
 // ---- host-side parameter logic (cloud_sky.gd) -------------------------------------------------
 void cs_settings_default(cs_sky_settings* s) {  // cloud_sky.gd:4-50
@@ -1118,6 +1284,11 @@ int cs_sky_composite_host(cs_sky* k, const cs_view* vw, float* out, size_t bytes
 // ---- oracle-only probes for the known-answer tests (tests/test_oracle_known_answers.py) --------
 // Not part of include/cloudsky.h; they expose the internal functions of the restatement so that
 // each can be pinned against an analytic answer derived from the shader source.
+// Study hook, oracle only (tests/hierarchical_study.py): stride 0 = the reference's fixed-step march.
+int cso_set_hierarchical(cs_context* c, int stride, float margin, int lod_bias) {
+    if (!c || stride < 0 || stride == 1 || stride > 32 || !(margin >= 0.0f) || margin > 1.0f || lod_bias < -8 || lod_bias > 8) return CS_ERR_INVALID;
+    c->hier_stride = stride; c->hier_margin = margin; c->hier_lod_bias = lod_bias; return CS_OK;
+}
 float cso_intersect_sphere(const float dir[3], float r) { return intersectSphere({0.0f, g_radius, 0.0f}, {dir[0], dir[1], dir[2]}, r); }
 float cso_hash(const float p[3]) { return hash3({p[0], p[1], p[2]}); }
 float cso_henyey_greenstein(float c, float g) { return henyey_greenstein(c, g); }

@@ -1,0 +1,199 @@
+"""Noise generator (cs_generate_noise; the reference README's TODO 3).
+
+CPU: the oracle's statement is checked against (i) a brute-force numpy Worley written from the definition, (ii) the texel
+arithmetic the CUDA kernel executes (csrc/noise_core.h compiled with g++ by tests/noise_host_check.cpp) byte for byte,
+(iii) tileability and the statistics the defaults aim for.  GPU: the kernel's bytes equal the oracle's, and a frame
+rendered from generated textures passes the usual parity gate."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HARNESS_SRC = os.path.join(ROOT, "tests", "noise_host_check.cpp")
+HARNESS_LIB = os.path.join(ROOT, "build", "libnoise_host_check.so")
+CORE_HDR = os.path.join(ROOT, "godot-volumetric-cloud-demo-v2_b200", "csrc", "noise_core.h")
+
+
+@pytest.fixture(scope="module")
+def harness(cs):
+    os.makedirs(os.path.dirname(HARNESS_LIB), exist_ok=True)
+    newest = max(os.path.getmtime(HARNESS_SRC), os.path.getmtime(CORE_HDR))
+    if not os.path.exists(HARNESS_LIB) or os.path.getmtime(HARNESS_LIB) < newest:
+        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-std=c++17", "-shared", "-o", HARNESS_LIB, HARNESS_SRC])
+    dll = C.CDLL(HARNESS_LIB)
+    dll.nzh_generate.restype = C.c_int
+    dll.nzh_generate.argtypes = [C.c_int, C.c_int, C.POINTER(cs.NoiseParams), C.c_void_p]
+
+    def gen(kind, n, params):
+        out = np.empty((n, n, 4) if kind == cs.NOISE_WEATHER else (n, n, n, 4), np.uint8)
+        assert dll.nzh_generate(kind, n, C.byref(params), out.ctypes.data) == 0
+        return out
+    return gen
+
+
+def _variants(cs, lib):
+    out = []
+    for kind, n in ((cs.NOISE_LARGE, 16), (cs.NOISE_SMALL, 16), (cs.NOISE_WEATHER, 64)):
+        out.append((kind, n, lib.noise_params_default(kind)))
+        p = lib.noise_params_default(kind)
+        p.seed = 0xDEADBEEF; p.worley_frequency = 3; p.worley_scale = 0.9; p.perlin_frequency = 5; p.perlin_octaves = 3
+        p.perlin_scale = 1.7; p.remap_lo = 0.3; p.remap_hi = 0.8; p.type_lo = 0.1; p.type_hi = 0.95
+        out.append((kind, n, p))
+    return out
+
+
+def test_kernel_arithmetic_matches_oracle_on_cpu(cs, oracle_lib, harness, helpers):
+    ctx = oracle_lib.context(0)
+    ctx.set_threads(helpers.cpu_threads)
+    for kind, n, p in _variants(cs, oracle_lib):
+        a = ctx.generate_noise(kind, n, p)
+        b = harness(kind, n, p)
+        assert (a == b).all(), f"kind {kind}: {int((a != b).sum())} bytes differ"
+    ctx.close()
+
+
+def _mix(h):
+    h &= 0xFFFFFFFF
+    h ^= h >> 16; h = (h * 0x7FEB352D) & 0xFFFFFFFF
+    h ^= h >> 15; h = (h * 0x846CA68B) & 0xFFFFFFFF
+    h ^= h >> 16
+    return h
+
+
+def _feature(cell, f, seed):
+    x, y, z = (c % f for c in cell)
+    h0 = _mix(x + _mix(y + _mix(z + _mix(seed))))
+    h1 = _mix(h0 + 0x9E3779B9)
+    h2 = _mix(h1 + 0x9E3779B9)
+    return np.array([(h >> 8) / 16777216.0 for h in (h0, h1, h2)])
+
+
+def test_worley_against_brute_force_definition(cs, oracle_lib):
+    """Small volume, red channel = fbm3 of inverted Worley F1 at frequencies f, 2f, 4f (float64 brute force over ALL cells)."""
+    ctx = oracle_lib.context(0)
+    p = oracle_lib.noise_params_default(cs.NOISE_SMALL)
+    p.seed = 42; p.worley_frequency = 2; p.worley_scale = 0.8
+    n = 8
+    vol = ctx.generate_noise(cs.NOISE_SMALL, n, p)
+    ctx.close()
+
+    def worley(pt, f, seed):
+        q = pt * f
+        best = 1e9
+        for cz in range(-1, f + 1):
+            for cy in range(-1, f + 1):
+                for cx in range(-1, f + 1):
+                    fp = np.array([cx, cy, cz]) + _feature((cx, cy, cz), f, seed)
+                    best = min(best, float(((fp - q) ** 2).sum()))
+        return 1.0 - min(np.sqrt(best) * 0.8, 1.0)
+
+    rng = np.random.default_rng(0)
+    for _ in range(12):
+        x, y, z = (int(v) for v in rng.integers(0, n, 3))
+        pt = (np.array([x, y, z]) + 0.5) / n
+        w = [worley(pt, 2 << k, 42 + 101 * k) for k in range(3)]
+        want = w[0] * 0.625 + w[1] * 0.25 + w[2] * 0.125
+        assert abs(int(vol[z, y, x, 0]) - want * 255.0) <= 0.51, (x, y, z)
+
+
+def test_tileable_and_statistics(cs, oracle_lib, helpers):
+    ctx = oracle_lib.context(0)
+    ctx.set_threads(helpers.cpu_threads)
+    large = ctx.generate_noise(cs.NOISE_LARGE, 32).astype(np.float32) / 255.0
+    small = ctx.generate_noise(cs.NOISE_SMALL, 32).astype(np.float32) / 255.0
+    weather = ctx.generate_noise(cs.NOISE_WEATHER, 256).astype(np.float32) / 255.0
+    ctx.close()
+    # the defaults aim at the reference bitmaps' channel means (0.85 / 0.71 / 0.71 / 0.71; small 0.71)
+    m = large.reshape(-1, 4).mean(0)
+    assert abs(m[0] - 0.85) < 0.04 and (np.abs(m[1:] - 0.71) < 0.04).all(), m
+    assert (np.abs(small.reshape(-1, 4).mean(0)[:3] - 0.71) < 0.04).all()
+    assert (small[..., 3] == 1.0).all() and (weather[..., 1] == 0.0).all() and (weather[..., 3] == 1.0).all()
+    t, cov = weather[..., 0], weather[..., 2]
+    assert t.min() >= 0.58 and t.max() <= 0.92 and cov.min() < 0.05 and cov.max() > 0.9
+    # tileable: the step across the wrap seam is no larger than the steps inside the tile, on every axis
+    for vol, axes in ((large, 3), (small, 3), (weather, 2)):
+        for ax in range(axes):
+            inner = np.abs(np.diff(vol, axis=ax)).max()
+            seam = np.abs(np.take(vol, 0, axis=ax) - np.take(vol, -1, axis=ax)).max()
+            assert seam <= inner + 1e-6, (ax, seam, inner)
+    # different seeds decorrelate
+    ctx = oracle_lib.context(0)
+    p = oracle_lib.noise_params_default(cs.NOISE_SMALL); p.seed = 2
+    other = ctx.generate_noise(cs.NOISE_SMALL, 32, p).astype(np.float32) / 255.0
+    ctx.close()
+    c = np.corrcoef(small[..., 0].ravel(), other[..., 0].ravel())[0, 1]
+    assert abs(c) < 0.2
+
+
+def test_bad_requests_are_rejected(cs, oracle_lib):
+    ctx = oracle_lib.context(0)
+    p = oracle_lib.noise_params_default(cs.NOISE_LARGE)
+    out = np.empty(16 ** 3 * 4, np.uint8)
+    call = lambda kind, n, pp, nbytes: oracle_lib.dll.cs_generate_noise(ctx._h, kind, n, C.byref(pp), out.ctypes.data, nbytes)
+    assert call(cs.NOISE_LARGE, 16, p, out.nbytes) == 0
+    assert call(cs.NOISE_LARGE, 12, p, 12 ** 3 * 4) != 0      # not a power of two
+    assert call(cs.NOISE_LARGE, 16, p, out.nbytes - 4) != 0   # wrong buffer size
+    assert call(7, 16, p, out.nbytes) != 0
+    p.perlin_octaves = 0
+    assert call(cs.NOISE_LARGE, 16, p, out.nbytes) != 0
+    p = oracle_lib.noise_params_default(cs.NOISE_WEATHER); p.remap_hi = p.remap_lo
+    assert call(cs.NOISE_WEATHER, 16, p, 16 * 16 * 4) != 0
+    ctx.close()
+
+
+def test_generated_textures_render(cs, oracle_lib, helpers):
+    """Generated volumes are valid inputs of the march: upload -> render gives a finite, partly cloudy hemisphere."""
+    ctx = oracle_lib.context(0)
+    ctx.set_threads(helpers.cpu_threads)
+    tex = (ctx.generate_noise(cs.NOISE_LARGE, 32), ctx.generate_noise(cs.NOISE_SMALL, 16), ctx.generate_noise(cs.NOISE_WEATHER, 128))
+    ctx.upload_textures(*tex)
+    ctx.build_transmittance_lut(); ctx.build_sky_lut((0.0, 1.0, 0.0)); ctx.resize(64, 32)
+    ctx.set_march_config(32, 3, cs.MODE_FAST)
+    ctx.render_frame(helpers.make_params(oracle_lib, 64, 32, coverage=0.5))
+    img = ctx.read_image().astype(np.float32)
+    ctx.close()
+    assert np.isfinite(img).all()
+    assert 0.02 < img[..., 3].mean() < 0.98
+
+
+@pytest.mark.gpu
+def test_gpu_generator_is_byte_identical_to_oracle(cs, oracle_lib, product_lib, helpers):
+    o = oracle_lib.context(0)
+    o.set_threads(helpers.cpu_threads)
+    g = product_lib.context(0)
+    cases = _variants(cs, oracle_lib) + [(cs.NOISE_LARGE, 64, oracle_lib.noise_params_default(cs.NOISE_LARGE)),
+                                        (cs.NOISE_SMALL, 32, oracle_lib.noise_params_default(cs.NOISE_SMALL)),
+                                        (cs.NOISE_WEATHER, 512, oracle_lib.noise_params_default(cs.NOISE_WEATHER))]
+    for kind, n, p in cases:
+        a, b = o.generate_noise(kind, n, p), g.generate_noise(kind, n, p)
+        assert (a == b).all(), f"kind {kind} n {n}: {int((a != b).sum())} bytes differ"
+    # defaults agree between the two libraries
+    for kind in (cs.NOISE_LARGE, cs.NOISE_SMALL, cs.NOISE_WEATHER):
+        assert bytes(oracle_lib.noise_params_default(kind)) == bytes(product_lib.noise_params_default(kind))
+    # validation
+    out = np.empty(16, np.uint8)
+    p = product_lib.noise_params_default(cs.NOISE_LARGE)
+    assert product_lib.dll.cs_generate_noise(g._h, cs.NOISE_LARGE, 12, C.byref(p), out.ctypes.data, 12 ** 3 * 4) == 1
+    assert b"power of two" in product_lib.dll.cs_last_error(g._h)
+    o.close(); g.close()
+
+
+@pytest.mark.gpu
+def test_gpu_render_from_generated_textures_matches_oracle(cs, oracle_lib, product_lib, helpers):
+    g = product_lib.context(0)
+    tex = (g.generate_noise(cs.NOISE_LARGE, 128), g.generate_noise(cs.NOISE_SMALL, 32), g.generate_noise(cs.NOISE_WEATHER, 512))
+    g.close()
+    W, H = 192, 96
+    imgs = []
+    for lib in (product_lib, oracle_lib):
+        ctx = helpers.prepared_context(lib, tex, W, H, threads=helpers.cpu_threads if lib is oracle_lib else None)
+        ctx.set_march_config(128, 6, cs.MODE_FAST)
+        ctx.render_frame(helpers.make_params(lib, W, H, coverage=0.35, time=3.0))
+        imgs.append(ctx.read_image().astype(np.float32))
+        ctx.close()
+    ok, mx = helpers.compare_images(imgs[0], imgs[1], 2e-3, 1e-2)
+    assert 0.02 < imgs[1][..., 3].mean() < 0.98
+    assert ok >= 0.999 and mx < 0.1, (ok, mx)
