@@ -120,6 +120,7 @@ class NoiseParams(C.Structure):
 
 
 NOISE_LARGE, NOISE_SMALL, NOISE_WEATHER = 0, 1, 2
+TLUT_LINEAR, TLUT_BRUNETON2017 = 0, 1  # cs_set_transmittance_parametrisation
 
 
 class View(C.Structure):
@@ -179,6 +180,7 @@ _PROTOTYPES = {
     "cs_read_volume_level": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_size_t]),
     "cs_noise_params_default": (None, [C.c_int, C.POINTER(NoiseParams)]),
     "cs_generate_noise": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(NoiseParams), _P, C.c_size_t]),
+    "cs_set_transmittance_parametrisation": (C.c_int, [_P, C.c_int]),
     "cs_build_transmittance_lut": (C.c_int, [_P]),
     "cs_build_sky_lut": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "cs_read_transmittance_lut": (C.c_int, [_P, _P, C.c_size_t]),
@@ -378,6 +380,9 @@ class Context:
         return out
 
     # LUTs ---------------------------------------------------------------------------------
+    def set_transmittance_parametrisation(self, which: int) -> None:
+        self._ck(self.lib.dll.cs_set_transmittance_parametrisation(self._h, which))
+
     def build_transmittance_lut(self) -> None:
         self._ck(self.lib.dll.cs_build_transmittance_lut(self._h))
 

@@ -4,6 +4,7 @@
 // it is compiled in the accurate configuration (--fmad=false, IEEE div/sqrt) to track the CPU oracle closely.
 #include "cs_context.h"
 #include "cs_device.cuh"
+#include "tlut_param.h"
 
 using namespace csd;
 
@@ -15,6 +16,7 @@ struct CompositeArgs {
     cs_view view;
     const uint16_t* clouds_from; const uint16_t* clouds_to; int tex_w, tex_h;
     const uint16_t* sky_from; const uint16_t* sky_to; const uint16_t* tlut;
+    int tlut_param;
     float4* out;
 };
 
@@ -94,7 +96,9 @@ __global__ void __launch_bounds__(128) composite_kernel(const __grid_constant__ 
             float c = dot3(V3{viewPos.x / height, viewPos.y / height, viewPos.z / height}, sun);
             float tu = 256.0f * clampf(0.5f + 0.5f * c, 0.0f, 1.0f) / 256.0f;
             float tv = 64.0f * fmaxf(0.0f, fminf(1.0f, (height - groundRadiusMM) / (atmosphereRadiusMM - groundRadiusMM))) / 64.0f;
-            V4 t = sample_lut_half4(A.tlut, CS_TRANSMITTANCE_W, CS_TRANSMITTANCE_H, tu, tv);
+            float visible = 1.0f;
+            if (A.tlut_param == CS_TLUT_BRUNETON2017) tl::bruneton_uv(tv, c, tu, tv, visible);  // same (mu, normalised altitude), other mapping
+            V4 t = sample_lut_half4(A.tlut, CS_TRANSMITTANCE_W, CS_TRANSMITTANCE_H, tu, tv) * visible;
             sunLum = {sunLum.x * t.x, sunLum.y * t.y, sunLum.z * t.z};
         }
     }
@@ -115,7 +119,7 @@ extern "C" int cs_composite(cs_context* c, const cs_view* vw, const void* cf, co
     if (vw->width < 1 || vw->height < 1 || tw < 1 || th < 1 || (vw->projection != CS_VIEW_EQUIRECT && vw->projection != CS_VIEW_PERSPECTIVE))
         return cs::ctx_fail(c, CS_ERR_INVALID, "cs_composite: bad view");
     if (cudaSetDevice(c->device) != cudaSuccess) return cs::ctx_fail(c, CS_ERR_CUDA, "cudaSetDevice");
-    CompositeArgs A{*vw, (const uint16_t*)cf, (const uint16_t*)ct, tw, th, (const uint16_t*)sf, (const uint16_t*)st, c->d_tlut, (float4*)out};
+    CompositeArgs A{*vw, (const uint16_t*)cf, (const uint16_t*)ct, tw, th, (const uint16_t*)sf, (const uint16_t*)st, c->d_tlut, c->tlut_param, (float4*)out};
     dim3 block(128), grid((vw->width + 15) / 16, (vw->height + 7) / 8);
     composite_kernel<<<grid, block, 0, c->stream>>>(A);
     cudaError_t e = cudaGetLastError();

@@ -401,7 +401,7 @@ int ctx_build_sky_lut_into(cs_context* c, const float sun[3], uint16_t* dst) {
     int r = bind(c);
     if (r) return r;
     if (c->timing_on) timing_mark(c, c->ev_sky, c->n_sky, 0);
-    launch_sky_lut(c->d_tlut, sun, dst, c->stream);
+    launch_sky_lut(c->d_tlut, c->tlut_param, sun, dst, c->stream);
     if (c->timing_on) timing_mark(c, c->ev_sky, c->n_sky++, 1);
     CU(cudaGetLastError());
     return CS_OK;
@@ -566,11 +566,18 @@ int cs_generate_noise(cs_context* c, int kind, int n, const cs_noise_params* P, 
     return CS_OK;
 }
 
+int cs_set_transmittance_parametrisation(cs_context* c, int which) {
+    if (!c) return CS_ERR_INVALID;
+    if (which != CS_TLUT_LINEAR && which != CS_TLUT_BRUNETON2017) return fail(c, CS_ERR_INVALID, "cs_set_transmittance_parametrisation: CS_TLUT_LINEAR or CS_TLUT_BRUNETON2017");
+    if (which != c->tlut_param) { c->tlut_param = which; c->have_tlut = false; c->have_sky = false; }  // both LUTs depend on the mapping
+    return CS_OK;
+}
+
 int cs_build_transmittance_lut(cs_context* c) {
     if (!c) return CS_ERR_INVALID;
     int r = bind(c);
     if (r) return r;
-    launch_transmittance_lut(c->d_tlut, c->stream);
+    launch_transmittance_lut(c->d_tlut, c->tlut_param, c->stream);
     CU(cudaGetLastError());
     c->have_tlut = true;
     return CS_OK;
@@ -581,7 +588,7 @@ int cs_build_sky_lut(cs_context* c, const float sun[3]) {
     int r = bind(c);
     if (r) return r;
     if (c->timing_on) timing_mark(c, c->ev_sky, c->n_sky, 0);
-    launch_sky_lut(c->d_tlut, sun, c->d_sky, c->stream);
+    launch_sky_lut(c->d_tlut, c->tlut_param, sun, c->d_sky, c->stream);
     if (c->timing_on) timing_mark(c, c->ev_sky, c->n_sky++, 1);
     CU(cudaGetLastError());
     c->have_sky = true;

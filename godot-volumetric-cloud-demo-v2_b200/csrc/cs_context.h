@@ -34,6 +34,7 @@ struct cs_context {
     uint16_t* d_tlut = nullptr;
     uint16_t* d_sky = nullptr;
     bool have_tlut = false, have_sky = false;
+    int tlut_param = CS_TLUT_LINEAR;  // cs_set_transmittance_parametrisation
     float* d_frame_consts = nullptr;
 
     // output

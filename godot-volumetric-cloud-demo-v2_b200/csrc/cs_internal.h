@@ -75,8 +75,8 @@ struct FrameConsts {
 };
 
 // kernel launchers (defined in the .cu files) — all asynchronous on `stream`.
-void launch_transmittance_lut(uint16_t* out_half4, void* stream);
-void launch_sky_lut(const uint16_t* transmittance_half4, const float sun_dir[3], uint16_t* out_half4, void* stream);
+void launch_transmittance_lut(uint16_t* out_half4, int parametrisation, void* stream);
+void launch_sky_lut(const uint16_t* transmittance_half4, int parametrisation, const float sun_dir[3], uint16_t* out_half4, void* stream);
 void launch_clouds_prologue(const CloudLaunch& L, bool strict, void* stream);
 void launch_clouds_strict(const CloudLaunch& L, void* stream);
 void launch_clouds_fast(const CloudLaunch& L, void* stream);

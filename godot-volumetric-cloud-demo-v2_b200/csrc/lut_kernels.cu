@@ -10,6 +10,7 @@
 // like the reference dispatch (transmittance_lut.gd:77 -> 32x8 groups).
 #include "cs_device.cuh"
 #include "cs_internal.h"
+#include "tlut_param.h"
 
 using namespace csd;
 
@@ -57,14 +58,20 @@ __device__ __forceinline__ Coeffs atmosphere_coefficients(float h) {
     return c;
 }
 
-__global__ void __launch_bounds__(64) transmittance_lut_kernel(uint16_t* __restrict__ out) {
+__global__ void __launch_bounds__(64) transmittance_lut_kernel(uint16_t* __restrict__ out, int param) {
     int px = blockIdx.x * 8 + threadIdx.x, py = blockIdx.y * 8 + threadIdx.y;
     if (px >= CS_TRANSMITTANCE_W || py >= CS_TRANSMITTANCE_H) return;
     float u = (float)px / (float)CS_TRANSMITTANCE_W, v = (float)py / (float)CS_TRANSMITTANCE_H;
     float sun_cos_theta = u * 2.0f - 1.0f;
+    float distance_to_earth_center = mixf(EARTH_RADIUS, ATMOSPHERE_RADIUS, v);
+    float t_d;
+    if (param == CS_TLUT_BRUNETON2017) {  // the texel stores the ray (r, mu) of Bruneton's mapping; its length to the top boundary is d
+        float h;
+        tl::bruneton_ray_from_texel(px, py, h, distance_to_earth_center, sun_cos_theta, t_d);
+    }
     V3 sun_dir = {-sqrtf(1.0f - sun_cos_theta * sun_cos_theta), 0.0f, sun_cos_theta};
-    V3 ray_origin = {0.0f, 0.0f, mixf(EARTH_RADIUS, ATMOSPHERE_RADIUS, v)};
-    float t_d = ray_sphere_intersection(ray_origin, sun_dir, ATMOSPHERE_RADIUS);
+    V3 ray_origin = {0.0f, 0.0f, distance_to_earth_center};
+    if (param != CS_TLUT_BRUNETON2017) t_d = ray_sphere_intersection(ray_origin, sun_dir, ATMOSPHERE_RADIUS);
     float dt = t_d / 40.0f;
     V4 result = splat4(0.0f);
     for (int i = 0; i < 40; ++i) {
@@ -80,10 +87,13 @@ __global__ void __launch_bounds__(64) transmittance_lut_kernel(uint16_t* __restr
 
 // Bilinear CLAMP_TO_EDGE fetch of the transmittance LUT from a shared-memory copy (same arithmetic as
 // sample_lut_half4; plain loads instead of __ldg).
+template <bool BRUNETON>
 __device__ __forceinline__ V4 transmittance_from_smem(const uint2* __restrict__ lut, float cos_theta, float normalized_altitude) {
     const int w = CS_TRANSMITTANCE_W, h = CS_TRANSMITTANCE_H;
     float su = clampf(cos_theta * 0.5f + 0.5f, 0.0f, 1.0f);
     float sv = clampf(normalized_altitude, 0.0f, 1.0f);
+    float visible = 1.0f;
+    if constexpr (BRUNETON) tl::bruneton_uv(normalized_altitude, cos_theta, su, sv, visible);
     float ux = su * (float)w - 0.5f, uy = sv * (float)h - 0.5f;
     float fx0 = floorf(ux), fy0 = floorf(uy);
     float fx = ux - fx0, fy = uy - fy0;
@@ -102,6 +112,7 @@ __device__ __forceinline__ V4 transmittance_from_smem(const uint2* __restrict__ 
         float a = lerpf(ch(t00, c), ch(t10, c), fx);
         float b = lerpf(ch(t01, c), ch(t11, c), fx);
         o[c] = lerpf(a, b, fy);
+        if constexpr (BRUNETON) o[c] = o[c] * visible;
     }
     return {o[0], o[1], o[2], o[3]};
 }
@@ -117,6 +128,7 @@ constexpr int kSkyLutBytes = CS_TRANSMITTANCE_W * CS_TRANSMITTANCE_H * 8;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+template <bool BRUNETON>
 __global__ void __launch_bounds__(32 * kSkyWarps, 1) sky_lut_kernel(const uint16_t* __restrict__ tlut, float sx, float sy, float sz,
                                                                     uint16_t* __restrict__ out) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -148,7 +160,7 @@ __global__ void __launch_bounds__(32 * kSkyWarps, 1) sky_lut_kernel(const uint16
     const V3 sun_dir = {-sx, -sz, sy};  // params.sun_direction.xzy with x and y negated (:221-223)
     const V4 irradiance = {1.679f, 1.828f, 1.986f, 1.307f};
     const float albedo_over_pi = 0.3f / PI;
-    const V4 T_1_0 = transmittance_from_smem(lut, 1.0f, 0.0f);  // loop-invariant fetch of :153
+    const V4 T_1_0 = transmittance_from_smem<BRUNETON>(lut, 1.0f, 0.0f);  // loop-invariant fetch of :153
     const int n_texels = CS_SKY_LUT_W * CS_SKY_LUT_H;
 
     for (int texel = blockIdx.x * kSkyWarps + warp; texel < n_texels; texel += gridDim.x * kSkyWarps) {
@@ -181,11 +193,11 @@ __global__ void __launch_bounds__(32 * kSkyWarps, 1) sky_lut_kernel(const uint16
             float normalized_altitude = altitude / ATMOSPHERE_THICKNESS;
             float sample_cos_theta = dot3(zenith_dir, sun_dir);
             Coeffs c = atmosphere_coefficients(altitude);
-            V4 T_sun = transmittance_from_smem(lut, sample_cos_theta, normalized_altitude);
+            V4 T_sun = transmittance_from_smem<BRUNETON>(lut, sample_cos_theta, normalized_altitude);
             // get_multiple_scattering (:144-164)
             float omega = 2.0f * PI * (1.0f - sqrtf(d * d - EARTH_RADIUS * EARTH_RADIUS) / d);
-            V4 T_to_ground = transmittance_from_smem(lut, sample_cos_theta, 0.0f);
-            V4 T_1_h = transmittance_from_smem(lut, 1.0f, normalized_altitude);
+            V4 T_to_ground = transmittance_from_smem<BRUNETON>(lut, sample_cos_theta, 0.0f);
+            V4 T_1_h = transmittance_from_smem<BRUNETON>(lut, 1.0f, normalized_altitude);
             V4 T_g2s = {T_1_0.x / T_1_h.x, T_1_0.y / T_1_h.y, T_1_0.z / T_1_h.z, T_1_0.w / T_1_h.w};
             V4 L_ground = (((splat4(albedo_over_pi) * (INV_4PI * omega)) * T_to_ground) * T_g2s) * sample_cos_theta;
             const V4 fit = {0.217f, 0.347f, 0.594f, 1.0f};
@@ -221,12 +233,12 @@ __global__ void __launch_bounds__(32 * kSkyWarps, 1) sky_lut_kernel(const uint16
 
 namespace cs {
 
-void launch_transmittance_lut(uint16_t* out, void* stream) {
+void launch_transmittance_lut(uint16_t* out, int param, void* stream) {
     dim3 grid(CS_TRANSMITTANCE_W / 8, CS_TRANSMITTANCE_H / 8), block(8, 8);  // 32 x 8 groups (transmittance_lut.gd:77)
-    transmittance_lut_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(out);
+    transmittance_lut_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(out, param);
 }
 
-void launch_sky_lut(const uint16_t* tlut, const float sun[3], uint16_t* out, void* stream) {
+void launch_sky_lut(const uint16_t* tlut, int param, const float sun[3], uint16_t* out, void* stream) {
     // The reference dispatches 25 x 13 groups of 8 x 8 (sky_lut.gd:140); here: one persistent CTA per SM, warp per texel.
     static int sm_count[64] = {};  // per device: SM count, and "opt-in shared memory size configured"
     int dev = 0;
@@ -235,10 +247,12 @@ void launch_sky_lut(const uint16_t* tlut, const float sun[3], uint16_t* out, voi
     if (sm_count[dev] == 0) {
         int sms = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaFuncSetAttribute(sky_lut_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSkyLutBytes);
+        cudaFuncSetAttribute(sky_lut_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSkyLutBytes);
+        cudaFuncSetAttribute(sky_lut_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSkyLutBytes);
         sm_count[dev] = sms > 0 ? sms : 148;
     }
-    sky_lut_kernel<<<sm_count[dev], 32 * kSkyWarps, kSkyLutBytes, (cudaStream_t)stream>>>(tlut, sun[0], sun[1], sun[2], out);
+    if (param == CS_TLUT_BRUNETON2017) sky_lut_kernel<true><<<sm_count[dev], 32 * kSkyWarps, kSkyLutBytes, (cudaStream_t)stream>>>(tlut, sun[0], sun[1], sun[2], out);
+    else sky_lut_kernel<false><<<sm_count[dev], 32 * kSkyWarps, kSkyLutBytes, (cudaStream_t)stream>>>(tlut, sun[0], sun[1], sun[2], out);
 }
 
 }  // namespace cs

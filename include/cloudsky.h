@@ -194,6 +194,17 @@ int cs_generate_noise(cs_context* ctx, int kind, int n, const cs_noise_params* p
 
 /* ---- atmosphere LUTs -------------------------------------------------------------------- */
 
+/* How the transmittance LUT maps (altitude, cosine of the sun zenith angle) to texels.
+ * CS_TLUT_LINEAR (default) is the reference's mapping: u = 0.5 + 0.5 cos, v = altitude / thickness, the integral running
+ * to the top boundary even through the planet (transmittance-lut.glsl:161-171, sky-lut.glsl:137-142, clouds.gdshader:77-85).
+ * CS_TLUT_BRUNETON2017 is the second TODO of the reference's README (README.md:29 "Use the transmittance LUT
+ * parametrization from Bruneton (2017)"): (r, mu) -> (x_r, x_mu) through the distance to the top boundary, texel centres on
+ * the ends of the unit range, only rays that miss the ground stored, the planet's shadow applied at lookup with a
+ * smoothstep over the sun's angular radius.  Same 256x64 RGBA16F texture, same 40-step integral, every consumer
+ * (sky-LUT build, presentation composite) switches with it.  Changing it invalidates both LUTs (rebuild them). */
+#define CS_TLUT_LINEAR 0
+#define CS_TLUT_BRUNETON2017 1
+int cs_set_transmittance_parametrisation(cs_context* ctx, int which);
 /* Replaces transmittance_lut.gd:_initialize_compute_code's one dispatch (32x8 groups,
  * transmittance_lut.gd:66-78) of transmittance-lut.glsl:157-196.  256x64 RGBA16F. */
 int cs_build_transmittance_lut(cs_context* ctx);

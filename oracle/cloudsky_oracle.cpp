@@ -278,15 +278,55 @@ void get_atmosphere_collision_coefficients(float h, V4& aerosol_absorption, V4& 
     extinction = aerosol_absorption + aerosol_scattering + molecular_absorption + molecular_scattering;
 }
 
+// CS_TLUT_BRUNETON2017 (extension: README.md:29 TODO; include/cloudsky.h): E. Bruneton 2017, "Precomputed Atmospheric
+// Scattering: a New Implementation" — transmittance texture coordinates from (r, mu) through the distance to the top
+// boundary, texel centres on the ends of the unit range, written with cancellation-free differences of squares.
+const float BRUNETON_H2 = ATMOSPHERE_THICKNESS * (ATMOSPHERE_RADIUS + EARTH_RADIUS);  // Rt^2 - Rg^2
+const float SUN_ANGULAR_RADIUS = 0.53f * 3.14159265358979f / 180.0f * 0.5f;           // half of clouds.gdshader:49's disc
+struct BrunetonRay { float altitude, r, mu, d; };
+BrunetonRay bruneton_texel_ray(int px, int py) {
+    float H = sqrtf(BRUNETON_H2);
+    float x_mu = (float)px / (float)(CS_TRANSMITTANCE_W - 1);
+    float x_r = (float)py / (float)(CS_TRANSMITTANCE_H - 1);
+    float rho = H * x_r;
+    BrunetonRay o;
+    o.r = sqrtf(rho * rho + EARTH_RADIUS * EARTH_RADIUS);
+    o.altitude = (rho * rho) / (o.r + EARTH_RADIUS);
+    float d_min = ATMOSPHERE_THICKNESS - o.altitude, d_max = rho + H;
+    o.d = d_min + x_mu * (d_max - d_min);
+    o.mu = o.d == 0.0f ? 1.0f : (BRUNETON_H2 - rho * rho - o.d * o.d) / (2.0f * o.r * o.d);
+    o.mu = clampf(o.mu, -1.0f, 1.0f);
+    return o;
+}
+// -> (u, v, visible fraction of the sun's disc)
+V3 bruneton_lookup_coords(float normalized_altitude, float mu) {
+    float H = sqrtf(BRUNETON_H2);
+    float h = clampf(normalized_altitude, 0.0f, 1.0f) * ATMOSPHERE_THICKNESS;
+    float r = EARTH_RADIUS + h;
+    float rho = sqrtf(h * (2.0f * EARTH_RADIUS + h));
+    float d_min = ATMOSPHERE_THICKNESS - h, d_max = rho + H;
+    float rmu = r * mu;
+    float discriminant = rmu * rmu + d_min * (ATMOSPHERE_RADIUS + r);  // r^2 (mu^2 - 1) + Rt^2
+    float d = fmaxf(sqrtf(fmaxf(discriminant, 0.0f)) - rmu, 0.0f);
+    float x_mu = clampf((d - d_min) / (d_max - d_min), 0.0f, 1.0f), x_r = rho / H;
+    float u = 0.5f / (float)CS_TRANSMITTANCE_W + x_mu * (1.0f - 1.0f / (float)CS_TRANSMITTANCE_W);
+    float v = 0.5f / (float)CS_TRANSMITTANCE_H + x_r * (1.0f - 1.0f / (float)CS_TRANSMITTANCE_H);
+    float sin_horizon = EARTH_RADIUS / r, cos_horizon = -(rho / r);
+    float visible = smoothstepf(-sin_horizon * SUN_ANGULAR_RADIUS, sin_horizon * SUN_ANGULAR_RADIUS, mu - cos_horizon);
+    return {u, v, visible};
+}
+
 // transmittance-lut.glsl:157-196, one texel
-void transmittance_texel(int px, int py, uint16_t* out4) {
+void transmittance_texel(int px, int py, uint16_t* out4, int param) {
     const int TRANSMITTANCE_STEPS = 40;  // :45
     float u = (float)px / (float)CS_TRANSMITTANCE_W, v = (float)py / (float)CS_TRANSMITTANCE_H;  // :162
     float sun_cos_theta = u * 2.0f - 1.0f;
-    V3 sun_dir = {-sqrtf(1.0f - sun_cos_theta * sun_cos_theta), 0.0f, sun_cos_theta};
     float distance_to_earth_center = mixf(EARTH_RADIUS, ATMOSPHERE_RADIUS, v);
+    BrunetonRay br{};
+    if (param == CS_TLUT_BRUNETON2017) { br = bruneton_texel_ray(px, py); sun_cos_theta = br.mu; distance_to_earth_center = br.r; }
+    V3 sun_dir = {-sqrtf(1.0f - sun_cos_theta * sun_cos_theta), 0.0f, sun_cos_theta};
     V3 ray_origin = {0.0f, 0.0f, distance_to_earth_center};
-    float t_d = ray_sphere_intersection(ray_origin, sun_dir, ATMOSPHERE_RADIUS);
+    float t_d = param == CS_TLUT_BRUNETON2017 ? br.d : ray_sphere_intersection(ray_origin, sun_dir, ATMOSPHERE_RADIUS);
     float dt = t_d / (float)TRANSMITTANCE_STEPS;
     V4 result = splat4(0.0f);
     for (int i = 0; i < TRANSMITTANCE_STEPS; ++i) {
@@ -318,7 +358,11 @@ float aerosol_phase_function(float c) {                                         
     float den = 1.0f + sky_gg + 2.0f * sky_g * c;
     return INV_4PI * (1.0f - sky_gg) / (den * sqrtf(den));
 }
-V4 transmittance_from_lut(const uint16_t* lut, float cos_theta, float normalized_altitude) {  // :137-142
+V4 transmittance_from_lut(const uint16_t* lut, float cos_theta, float normalized_altitude, int param) {  // :137-142
+    if (param == CS_TLUT_BRUNETON2017) {
+        V3 c = bruneton_lookup_coords(normalized_altitude, cos_theta);
+        return sample_lut(lut, CS_TRANSMITTANCE_W, CS_TRANSMITTANCE_H, c.x, c.y) * c.z;
+    }
     float u = clampf(cos_theta * 0.5f + 0.5f, 0.0f, 1.0f);
     float v = clampf(normalized_altitude, 0.0f, 1.0f);
     return sample_lut(lut, CS_TRANSMITTANCE_W, CS_TRANSMITTANCE_H, u, v);
@@ -327,7 +371,7 @@ V4 transmittance_from_lut(const uint16_t* lut, float cos_theta, float normalized
 V4 ground_albedo_over_pi() { return {0.3f / SKY_PI, 0.3f / SKY_PI, 0.3f / SKY_PI, 0.3f / SKY_PI}; }
 
 // sky-lut.glsl:219-276
-V4 compute_inscattering(const uint16_t* tlut, V3 sun_direction_param, V3 ray_origin, V3 ray_dir, float t_d) {
+V4 compute_inscattering(const uint16_t* tlut, int param, V3 sun_direction_param, V3 ray_origin, V3 ray_dir, float t_d) {
     const int IN_SCATTERING_STEPS = 30;  // :53
     // :221-223  sun_dir = params.sun_direction.xzy; x = -x; y = -y
     V3 sun_dir = {-sun_direction_param.x, -sun_direction_param.z, sun_direction_param.y};
@@ -348,14 +392,14 @@ V4 compute_inscattering(const uint16_t* tlut, V3 sun_direction_param, V3 ray_ori
         float sample_cos_theta = dot3(zenith_dir, sun_dir);
         V4 aa, as, ma, msc, ext;
         get_atmosphere_collision_coefficients(altitude, aa, as, ma, msc, ext);
-        V4 transmittance_to_sun = transmittance_from_lut(tlut, sample_cos_theta, normalized_altitude);
+        V4 transmittance_to_sun = transmittance_from_lut(tlut, sample_cos_theta, normalized_altitude, param);
         // get_multiple_scattering (:144-164) inlined with GLSL's left-to-right order
         V4 ms;
         {
             float d = distance_to_earth_center;
             float omega = 2.0f * SKY_PI * (1.0f - sqrtf(d * d - EARTH_RADIUS * EARTH_RADIUS) / d);
-            V4 T_to_ground = transmittance_from_lut(tlut, sample_cos_theta, 0.0f);
-            V4 T_ground_to_sample = transmittance_from_lut(tlut, 1.0f, 0.0f) / transmittance_from_lut(tlut, 1.0f, normalized_altitude);
+            V4 T_to_ground = transmittance_from_lut(tlut, sample_cos_theta, 0.0f, param);
+            V4 T_ground_to_sample = transmittance_from_lut(tlut, 1.0f, 0.0f, param) / transmittance_from_lut(tlut, 1.0f, normalized_altitude, param);
             V4 L_ground = (((ground_albedo_over_pi() * (PHASE_ISOTROPIC * omega)) * T_to_ground) * T_ground_to_sample) * sample_cos_theta;
             V4 fit = {0.217f, 0.347f, 0.594f, 1.0f};
             V4 L_ms = (fit * 0.02f) * (1.0f / (1.0f + 5.0f * expf(-17.92f * sample_cos_theta)));
@@ -373,7 +417,7 @@ V4 compute_inscattering(const uint16_t* tlut, V3 sun_direction_param, V3 ray_ori
 }
 
 // sky-lut.glsl:278-315, one texel
-void sky_texel(const uint16_t* tlut, V3 sun_direction, int px, int py, uint16_t* out4) {
+void sky_texel(const uint16_t* tlut, int param, V3 sun_direction, int px, int py, uint16_t* out4) {
     float u = (float)px / (float)CS_SKY_LUT_W, v = (float)py / (float)CS_SKY_LUT_H;  // :284
     float azimuth = 2.0f * SKY_PI * u;
     float l = v * 2.0f - 1.0f;
@@ -383,7 +427,7 @@ void sky_texel(const uint16_t* tlut, V3 sun_direction, int px, int py, uint16_t*
     float atmos_dist = ray_sphere_intersection(ray_origin, ray_dir, ATMOSPHERE_RADIUS);
     float ground_dist = ray_sphere_intersection(ray_origin, ray_dir, EARTH_RADIUS);
     float t_d = ground_dist < 0.0f ? atmos_dist : ground_dist;
-    V4 L = compute_inscattering(tlut, sun_direction, ray_origin, ray_dir, t_d);
+    V4 L = compute_inscattering(tlut, param, sun_direction, ray_origin, ray_dir, t_d);
     // linear_srgb_from_spectral_samples: mat4x3 M * L, column-major (:207-217)
     const float M[4][3] = {{137.672389239975f, -8.632904716299537f, -1.7181567391931372f},
                            {32.549094028629234f, 91.29801417199785f, -12.005406444382531f},
@@ -662,6 +706,7 @@ struct cs_context {
     Volume large, small;
     Image8 weather;
     bool have_tex = false, have_tlut = false, have_sky = false;
+    int tlut_param = CS_TLUT_LINEAR;
     std::vector<uint16_t> tlut = std::vector<uint16_t>((size_t)CS_TRANSMITTANCE_W * CS_TRANSMITTANCE_H * 4);
     std::vector<uint16_t> skylut = std::vector<uint16_t>((size_t)CS_SKY_LUT_W * CS_SKY_LUT_H * 4);
     int W = 0, H = 0;
@@ -724,9 +769,14 @@ int cs_read_volume_level(cs_context* c, int which, int level, uint8_t* out, size
 int cs_build_transmittance_lut(cs_context* c) {
     if (!c) return CS_ERR_INVALID;
     parallel_rows(c->threads, CS_TRANSMITTANCE_H, [&](int y, int) {
-        for (int x = 0; x < CS_TRANSMITTANCE_W; x++) transmittance_texel(x, y, &c->tlut[((size_t)y * CS_TRANSMITTANCE_W + x) * 4]);
+        for (int x = 0; x < CS_TRANSMITTANCE_W; x++) transmittance_texel(x, y, &c->tlut[((size_t)y * CS_TRANSMITTANCE_W + x) * 4], c->tlut_param);
     });
     c->have_tlut = true;
+    return CS_OK;
+}
+int cs_set_transmittance_parametrisation(cs_context* c, int which) {
+    if (!c || (which != CS_TLUT_LINEAR && which != CS_TLUT_BRUNETON2017)) return fail(c, CS_ERR_INVALID, "cs_set_transmittance_parametrisation: CS_TLUT_LINEAR or CS_TLUT_BRUNETON2017");
+    if (which != c->tlut_param) { c->tlut_param = which; c->have_tlut = false; c->have_sky = false; }  // both LUTs depend on the mapping
     return CS_OK;
 }
 int cs_build_sky_lut(cs_context* c, const float sun[3]) {
@@ -734,7 +784,7 @@ int cs_build_sky_lut(cs_context* c, const float sun[3]) {
     if (!c->have_tlut) return fail(c, CS_ERR_NOT_READY, "Attempting to update uninitialized sky lut (no transmittance LUT)");
     V3 s = {sun[0], sun[1], sun[2]};
     parallel_rows(c->threads, CS_SKY_LUT_H, [&](int y, int) {
-        for (int x = 0; x < CS_SKY_LUT_W; x++) sky_texel(c->tlut.data(), s, x, y, &c->skylut[((size_t)y * CS_SKY_LUT_W + x) * 4]);
+        for (int x = 0; x < CS_SKY_LUT_W; x++) sky_texel(c->tlut.data(), c->tlut_param, s, x, y, &c->skylut[((size_t)y * CS_SKY_LUT_W + x) * 4]);
     });
     c->have_sky = true;
     return CS_OK;
@@ -1203,7 +1253,7 @@ float gd_ray_intersect_sphere(V3 ro, V3 rd, float rad) {
     return -b - sqrtf(discr);
 }
 // clouds.gdshader:87-102
-V3 gd_get_atmo(const uint16_t* sky_from, const uint16_t* sky_to, const uint16_t* tlut, float blend, V3 dir, V3 sun, float disk_scale) {
+V3 gd_get_atmo(const uint16_t* sky_from, const uint16_t* sky_to, const uint16_t* tlut, int tlut_param, float blend, V3 dir, V3 sun, float disk_scale) {
     const float groundRadiusMM = 6.360f, atmosphereRadiusMM = 6.460f;
     const V3 viewPos = {0.0f, groundRadiusMM + 0.0002f, 0.0f};
     V3 col = gd_sky_lut(sky_from, sky_to, blend, dir);
@@ -1219,6 +1269,7 @@ V3 gd_get_atmo(const uint16_t* sky_from, const uint16_t* sky_to, const uint16_t*
             float u = 256.0f * clampf(0.5f + 0.5f * c, 0.0f, 1.0f) / 256.0f;
             float v = 64.0f * fmaxf(0.0f, fminf(1.0f, (height - groundRadiusMM) / (atmosphereRadiusMM - groundRadiusMM))) / 64.0f;
             V4 t = sample_half4_clamp(tlut, CS_TRANSMITTANCE_W, CS_TRANSMITTANCE_H, u, v);
+            if (tlut_param == CS_TLUT_BRUNETON2017) t = transmittance_from_lut(tlut, c, v, tlut_param);  // same (mu, normalised altitude), other mapping
             sunLum = sunLum * V3{t.x, t.y, t.z};
         }
     }
@@ -1239,7 +1290,7 @@ V3 view_direction(const cs_view& vw, int x, int y) {
 }
 // sky() (clouds.gdshader:104-116)
 V3 gd_sky_pixel(const cs_view& vw, const uint16_t* cf, const uint16_t* ct, int tw, int th, const uint16_t* sf, const uint16_t* st,
-                const uint16_t* tlut, V3 eyedir) {
+                const uint16_t* tlut, int tlut_param, V3 eyedir) {
     V3 norm = eyedir;
     norm.y = fmaxf(0.0f, norm.y);
     norm = normalize3(norm);
@@ -1248,7 +1299,7 @@ V3 gd_sky_pixel(const cs_view& vw, const uint16_t* cf, const uint16_t* ct, int t
     float k = vw.blend_amount;
     V4 clouds = {mixf(a.x, b.x, k), mixf(a.y, b.y, k), mixf(a.z, b.z, k), mixf(a.w, b.w, k)};
     V3 sun = {vw.sun_direction[0], vw.sun_direction[1], vw.sun_direction[2]};
-    V3 background = gd_get_atmo(sf, st, tlut, k, eyedir, sun, vw.sun_disk_scale);
+    V3 background = gd_get_atmo(sf, st, tlut, tlut_param, k, eyedir, sun, vw.sun_disk_scale);
     V3 color = background * (1.0f - clouds.w) + V3{clouds.x, clouds.y, clouds.z};
     float f = smoothstepf(0.6f, 1.0f, 1.0f - eyedir.y);
     auto cl = [](float v) { return clampf(v, 0.0f, 100.0f); };
@@ -1265,7 +1316,7 @@ int cs_composite(cs_context* c, const cs_view* vw, const void* cf, const void* c
         return fail(c, CS_ERR_INVALID, "cs_composite: bad view");
     parallel_rows(c->threads, vw->height, [&](int y, int) {
         for (int x = 0; x < vw->width; x++) {
-            V3 col = gd_sky_pixel(*vw, (const uint16_t*)cf, (const uint16_t*)ct, tw, th, (const uint16_t*)sf, (const uint16_t*)st, c->tlut.data(), view_direction(*vw, x, y));
+            V3 col = gd_sky_pixel(*vw, (const uint16_t*)cf, (const uint16_t*)ct, tw, th, (const uint16_t*)sf, (const uint16_t*)st, c->tlut.data(), c->tlut_param, view_direction(*vw, x, y));
             float* o = out + ((size_t)y * vw->width + x) * 4;
             o[0] = col.x; o[1] = col.y; o[2] = col.z; o[3] = 1.0f;
         }
@@ -1284,6 +1335,15 @@ int cs_sky_composite_host(cs_sky* k, const cs_view* vw, float* out, size_t bytes
 // ---- oracle-only probes for the known-answer tests (tests/test_oracle_known_answers.py) --------
 // Not part of include/cloudsky.h; they expose the internal functions of the restatement so that
 // each can be pinned against an analytic answer derived from the shader source.
+// transmittance_from_lut (sky-lut.glsl:137-142) through the context's LUT and parametrisation.
+int cso_transmittance_lookup(cs_context* c, float cos_theta, float normalized_altitude, float out[4]) {
+    if (!c || !c->have_tlut) return CS_ERR_NOT_READY;
+    V4 t = transmittance_from_lut(c->tlut.data(), cos_theta, normalized_altitude, c->tlut_param);
+    out[0] = t.x; out[1] = t.y; out[2] = t.z; out[3] = t.w;
+    return CS_OK;
+}
+void cso_bruneton_texel_ray(int px, int py, float out[4]) { BrunetonRay b = bruneton_texel_ray(px, py); out[0] = b.altitude; out[1] = b.r; out[2] = b.mu; out[3] = b.d; }
+void cso_bruneton_lookup_coords(float normalized_altitude, float mu, float out[3]) { V3 c = bruneton_lookup_coords(normalized_altitude, mu); out[0] = c.x; out[1] = c.y; out[2] = c.z; }
 // Study hook, oracle only (tests/hierarchical_study.py): stride 0 = the reference's fixed-step march.
 int cso_set_hierarchical(cs_context* c, int stride, float margin, int lod_bias) {
     if (!c || stride < 0 || stride == 1 || stride > 32 || !(margin >= 0.0f) || margin > 1.0f || lod_bias < -8 || lod_bias > 8) return CS_ERR_INVALID;
