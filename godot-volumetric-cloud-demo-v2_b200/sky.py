@@ -42,11 +42,13 @@ class TransmittanceLUT:
     """transmittance_lut.gd: a 256x64 RGBA16F texture generated once when loaded."""
     texture_size = (capi.TRANSMITTANCE_W, capi.TRANSMITTANCE_H)  # transmittance_lut.gd:6
 
-    def __init__(self, ctx: capi.Context):
+    def __init__(self, ctx: capi.Context, parametrisation: int = capi.TLUT_LINEAR):
         self.ctx = ctx
+        self.parametrisation = parametrisation  # TLUT_BRUNETON2017: the mapping the reference's README lists as a TODO (README.md:29)
         self._initialize_compute_code()
 
     def _initialize_compute_code(self) -> None:  # transmittance_lut.gd:51-78: one dispatch of 32x8 groups
+        self.ctx.set_transmittance_parametrisation(self.parametrisation)
         self.ctx.build_transmittance_lut()
 
     def read(self) -> np.ndarray:
@@ -160,6 +162,15 @@ class CloudSky:
         self.ctx.upload_textures(large, small, weather)  # _create_noise_uniform_set (cloud_sky.gd:298-341)
         self._have_textures = True
         self.can_run = True
+
+    def generate_textures(self, seed: int = 1, large_n: int = 128, small_n: int = 32, weather_n: int = 512) -> None:
+        """Synthesise the three inputs on the device instead of loading the bitmaps (the reference's TODO, README.md:30)."""
+        tex = []
+        for kind, n in ((capi.NOISE_LARGE, large_n), (capi.NOISE_SMALL, small_n), (capi.NOISE_WEATHER, weather_n)):
+            p = self.lib.noise_params_default(kind)
+            p.seed = seed
+            tex.append(self.ctx.generate_noise(kind, n, p))
+        self.load_textures(*tex)
 
     def load_texture_files(self, directory: str) -> None:  # preload("perlworlnoise.tga") ... (cloud_sky.gd:311,321,331)
         import os

@@ -18,6 +18,32 @@ def test_cli_builds_and_prints_usage():
     assert out.returncode == 0 and "usage: cloudsky_cli" in out.stdout
 
 
+def test_cli_procedural_inputs_through_any_backend(cs, oracle_lib, helpers, tmp_path):
+    """--procedural: cs_generate_noise -> cs_upload_textures -> render, here through the oracle's implementation of the ABI
+    (the driver only sees include/cloudsky.h); must equal the same calls made from Python."""
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "tools"), "-s"])
+    out_f16 = tmp_path / "out.f16"
+    W, H = 48, 24
+    r = subprocess.run([CLI, "--lib", oracle_lib.path, "--procedural", "5", "32", "16", "64", "--bruneton", "--size", str(W), str(H), "--steps", "24", "3",
+                        "--sun", "0", "1", "0", "--coverage", "0.5", "--out", str(out_f16)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "backend oracle-cpu" in r.stdout
+    got = np.fromfile(out_f16, dtype=np.float16).reshape(H, W, 4)
+    ctx = oracle_lib.context(0)
+    ctx.set_threads(helpers.cpu_threads)
+    tex = []
+    for kind, n in ((cs.NOISE_LARGE, 32), (cs.NOISE_SMALL, 16), (cs.NOISE_WEATHER, 64)):
+        p = oracle_lib.noise_params_default(kind); p.seed = 5
+        tex.append(ctx.generate_noise(kind, n, p))
+    ctx.upload_textures(*tex)
+    ctx.set_transmittance_parametrisation(cs.TLUT_BRUNETON2017)
+    ctx.build_transmittance_lut(); ctx.resize(W, H); ctx.set_march_config(24, 3, cs.MODE_FAST)
+    want = ctx.render_frame_host(helpers.make_params(oracle_lib, W, H, coverage=0.5))
+    ctx.close()
+    assert (got.view(np.uint16) == want.view(np.uint16)).all()
+    assert 0.02 < float(got[..., 3].astype(np.float32).mean()) < 0.98
+
+
 @pytest.mark.gpu
 def test_cli_matches_python_path(cs, product_lib, textures, helpers, tmp_path):
     sys.path.insert(0, os.path.join(ROOT, "tests"))

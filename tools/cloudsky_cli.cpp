@@ -4,7 +4,9 @@
 // --lib), decodes the three input bitmaps, builds both atmosphere LUTs, renders the hemisphere
 // texture for the given sun / wind settings and writes it as raw half4 (.f16) and/or a tonemapped
 // PPM preview.  It plays the role of cloud_sky.gd's _update_per_frame_data + _render_process
-// (cloud_sky.gd:165-187,234-248) for a headless caller.
+// (cloud_sky.gd:165-187,234-248) for a headless caller.  --procedural SEED LARGE_N SMALL_N WEATHER_N replaces the bitmaps by
+// noise synthesised on the device (cs_generate_noise, the reference README's TODO 3); --bruneton selects the Bruneton 2017
+// transmittance-LUT mapping (README TODO 2); --flags N ORs march-mode flags (2 early out, 4 texture unit) into the mode.
 #include <dlfcn.h>
 
 #include <chrono>
@@ -31,6 +33,8 @@ int main(int argc, char** argv) {
     std::string lib = "godot-volumetric-cloud-demo-v2_b200/csrc/libcloudsky_b200.so", dir = "cloud_sky", out_f16, out_ppm;
     int W = 768, H = 768, P = CS_REF_PRIMARY_STEPS, cone = CS_REF_CONE_SAMPLES, mode = CS_MODE_FAST, device = 0, iters = 1;
     float sun[3] = {0.0f, 1.0f, 0.0f}, time_s = 0.0f, coverage = -1.0f, density = -1.0f, wind_dir = 0.0f, wind_speed = 1.0f;
+    int procedural = 0, gen_n[3] = {128, 32, 512}, tlut_mapping = CS_TLUT_LINEAR, flags = 0;
+    unsigned seed = 1;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         auto next = [&]() -> const char* { return i + 1 < argc ? argv[++i] : ""; };
@@ -46,11 +50,15 @@ int main(int argc, char** argv) {
         else if (a == "--density") density = (float)atof(next());
         else if (a == "--wind") { wind_dir = (float)atof(next()); wind_speed = (float)atof(next()); }
         else if (a == "--iters") iters = atoi(next());
+        else if (a == "--procedural") { procedural = 1; seed = (unsigned)strtoul(next(), nullptr, 0); for (int k = 0; k < 3; k++) gen_n[k] = atoi(next()); }
+        else if (a == "--bruneton") tlut_mapping = CS_TLUT_BRUNETON2017;
+        else if (a == "--flags") flags = atoi(next());
         else if (a == "--out") out_f16 = next();
         else if (a == "--ppm") out_ppm = next();
         else {
             printf("usage: cloudsky_cli [--lib so] [--assets dir] [--size W H] [--steps P cone] [--strict] [--device n]\n"
-                   "       [--sun x y z] [--time s] [--coverage c] [--density d] [--wind dir_rad speed] [--iters n] [--out img.f16] [--ppm img.ppm]\n");
+                   "       [--sun x y z] [--time s] [--coverage c] [--density d] [--wind dir_rad speed] [--iters n] [--out img.f16] [--ppm img.ppm]\n"
+                   "       [--procedural seed large_n small_n weather_n] [--bruneton] [--flags march_mode_flags]\n");
             return a == "--help" ? 0 : 1;
         }
     }
@@ -58,15 +66,27 @@ int main(int argc, char** argv) {
     if (!h) { fprintf(stderr, "dlopen(%s): %s\n", lib.c_str(), dlerror()); return 2; }
     SYM(cs_create) SYM(cs_destroy) SYM(cs_last_error) SYM(cs_backend_name) SYM(cs_load_texture_files) SYM(cs_build_transmittance_lut)
     SYM(cs_build_sky_lut) SYM(cs_resize) SYM(cs_set_march_config) SYM(cs_render_frame_host) SYM(cs_settings_demo) SYM(cs_frame_state_init)
-    SYM(cs_frame_advance) SYM(cs_fill_cloud_params)
+    SYM(cs_frame_advance) SYM(cs_fill_cloud_params) SYM(cs_generate_noise) SYM(cs_noise_params_default) SYM(cs_upload_textures)
+    SYM(cs_set_transmittance_parametrisation)
 
     cs_context* ctx = nullptr;
     if (cs_create(device, &ctx) != CS_OK) { fprintf(stderr, "cs_create failed (backend %s)\n", cs_backend_name()); return 3; }
 #define CK(call) do { int r__ = (call); if (r__ != CS_OK) { fprintf(stderr, "%s -> %d: %s\n", #call, r__, cs_last_error(ctx)); cs_destroy(ctx); return 3; } } while (0)
-    CK(cs_load_texture_files(ctx, (dir + "/perlworlnoise.tga").c_str(), 128, (dir + "/worlnoise.bmp").c_str(), 32, (dir + "/weather.bmp").c_str()));
+    if (procedural) {  // synthesise the three inputs instead of preload()-ing the bitmaps
+        std::vector<uint8_t> tex[3];
+        for (int k = 0; k < 3; k++) {
+            cs_noise_params np; cs_noise_params_default(k, &np); np.seed = seed;
+            tex[k].resize((size_t)gen_n[k] * gen_n[k] * (k == CS_NOISE_WEATHER ? 1 : gen_n[k]) * 4);
+            CK(cs_generate_noise(ctx, k, gen_n[k], &np, tex[k].data(), tex[k].size()));
+        }
+        CK(cs_upload_textures(ctx, tex[0].data(), gen_n[0], 4, tex[1].data(), gen_n[1], 4, tex[2].data(), gen_n[2], gen_n[2], 4));
+    } else {
+        CK(cs_load_texture_files(ctx, (dir + "/perlworlnoise.tga").c_str(), 128, (dir + "/worlnoise.bmp").c_str(), 32, (dir + "/weather.bmp").c_str()));
+    }
+    CK(cs_set_transmittance_parametrisation(ctx, tlut_mapping));
     CK(cs_build_transmittance_lut(ctx));
     CK(cs_resize(ctx, W, H));
-    CK(cs_set_march_config(ctx, P, cone, mode));
+    CK(cs_set_march_config(ctx, P, cone, mode == CS_MODE_STRICT ? mode : (mode | flags)));
     cs_sky_settings s; cs_settings_demo(&s);
     if (coverage >= 0) s.cloud_coverage = coverage;
     if (density >= 0) s.density = density;
