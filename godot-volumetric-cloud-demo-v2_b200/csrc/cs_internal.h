@@ -61,6 +61,9 @@ struct CloudLaunch {
     const float* frame_consts;                  // FrameConsts written by the prologue kernel
     uint16_t* out;                              // half4 image
     unsigned long long* counters;               // 6 x u64 or nullptr
+    float band_lo, band_hi;                     // density() is exactly 0 for height fractions outside (band_lo, band_hi) (context.cu: height_band)
+    unsigned int* tickets;                      // persistent-warp variant of the fast kernel: one patch-ticket counter per SM slot (zeroed by the launcher)
+    int sm_slots;                               // number of SMs of the device
 };
 
 // Pixel-independent values of march()'s prologue (clouds.glsl:149-167), computed once per

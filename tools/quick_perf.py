@@ -7,7 +7,7 @@ import cloudsky_b200 as cs
 from cloudsky_b200 import assets
 
 def main():
-    lib = cs.load_product()
+    lib = cs.Library(sys.argv[sys.argv.index("--lib") + 1]) if "--lib" in sys.argv else cs.load_product()  # --lib: a variant built by tools/build_variants.sh
     large, small, weather, desc = assets.load_default_textures()
     res = []
     cfgs = [(2048, 1024, 128, 6, 0.2), (2048, 1024, 128, 7, 0.2), (2048, 1024, 128, 7, 1.0), (1024, 512, 64, 5, 0.2)]
