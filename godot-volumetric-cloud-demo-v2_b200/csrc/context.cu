@@ -399,6 +399,7 @@ int make_launch(cs_context* c, const cs_cloud_params* P, int x0, int y0, int x1,
     L.counters = c->counters_on ? c->d_counters : nullptr;
     if (c->band_coverage != P->cloud_coverage) { height_band(c, P->cloud_coverage, &c->band_lo, &c->band_hi); c->band_coverage = P->cloud_coverage; }
     L.band_lo = c->band_lo; L.band_hi = c->band_hi;
+    L.n_suns = 1; L.sun_stride_px = 0;
     L.tickets = c->d_tickets;
     L.sm_slots = c->sm_count;
     return CS_OK;
@@ -470,7 +471,8 @@ int cs_create(int device, cs_context** out) {
     bool ok = cudaSetDevice(device) == cudaSuccess && cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaMalloc(&c->d_tlut, (size_t)CS_TRANSMITTANCE_W * CS_TRANSMITTANCE_H * 8) == cudaSuccess &&
               cudaMalloc(&c->d_sky, (size_t)CS_SKY_LUT_W * CS_SKY_LUT_H * 8) == cudaSuccess &&
-              cudaMalloc(&c->d_frame_consts, sizeof(FrameConsts)) == cudaSuccess &&
+              cudaMalloc(&c->d_frame_consts, sizeof(FrameConsts) * kMaxSunBatch) == cudaSuccess &&
+              cudaMalloc(&c->d_sky_batch, (size_t)CS_SKY_LUT_W * CS_SKY_LUT_H * 8 * kMaxSunBatch) == cudaSuccess &&
               cudaMalloc(&c->d_counters, 6 * sizeof(unsigned long long)) == cudaSuccess &&
               cudaMalloc(&c->d_tickets, 1024 * sizeof(unsigned int)) == cudaSuccess &&
               cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && c->sm_count > 0 && c->sm_count <= 1024;
@@ -480,6 +482,7 @@ int cs_create(int device, cs_context** out) {
         return CS_ERR_CUDA;
     }
     c->stream = c->own_stream;
+    if (const char* e = getenv("CLOUDSKY_SUN_BATCH")) c->sun_batching = e[0] != '0';  // development knob: 0 = one launch per sun
     *out = c;
     return CS_OK;
 }
@@ -494,6 +497,7 @@ void cs_destroy(cs_context* c) {
     if (c->d_frame_consts) cudaFree(c->d_frame_consts);
     if (c->d_counters) cudaFree(c->d_counters);
     if (c->d_tickets) cudaFree(c->d_tickets);
+    if (c->d_sky_batch) cudaFree(c->d_sky_batch);
     if (c->d_image) cudaFree(c->d_image);
     for (auto e : c->ev_march) cudaEventDestroy(e);
     for (auto e : c->ev_sky) cudaEventDestroy(e);
@@ -808,13 +812,41 @@ int cs_wait_host(cs_context* c) {
 }
 int cs_render_sun_batch_to(cs_context* c, const cs_cloud_params* P, const float* suns, int n, void* out) {
     if (!c || !P || !suns || !out || n < 1) return CS_ERR_INVALID;
-    for (int i = 0; i < n; i++) {
-        cs_cloud_params q = *P;
-        memcpy(q.light_direction, suns + 3 * i, 12);
-        int r = cs_build_sky_lut(c, q.light_direction);
-        if (r) return r;
-        r = dispatch(c, &q, 0, 0, c->W, c->H, (uint16_t*)out + (size_t)i * c->W * c->H * 4);
-        if (r) return r;
+    const size_t image_px = (size_t)c->W * c->H;
+    // CS_MODE_FAST with the record sampler: up to kMaxSunBatch suns share one march (clouds_fast_sunbatch_kernel) — the primary
+    // loop is sun-independent.  Other modes, instrumented runs and step counts beyond the tables: one launch per sun.
+    const bool batched = c->mode == CS_MODE_FAST && !c->counters_on && !c->timing_on && c->cone_samples + 1 <= 16 && n > 1 && c->have_tlut && c->sun_batching;
+    int i = 0;
+    while (i < n) {
+        const int k = batched ? std::min(n - i, (int)kMaxSunBatch) : 1;
+        if (k == 1) {
+            cs_cloud_params q = *P;
+            memcpy(q.light_direction, suns + 3 * i, 12);
+            int r = cs_build_sky_lut(c, q.light_direction);
+            if (r) return r;
+            r = dispatch(c, &q, 0, 0, c->W, c->H, (uint16_t*)out + (size_t)i * image_px * 4);
+            if (r) return r;
+        } else {
+            int r = bind(c);
+            if (r) return r;
+            CloudLaunch L;
+            for (int s = 0; s < k; s++) {  // one sky LUT and one prologue (FrameConsts) per sun, exactly as for a single frame
+                cs_cloud_params q = *P;
+                memcpy(q.light_direction, suns + 3 * (i + s), 12);
+                uint16_t* lut = c->d_sky_batch + (size_t)s * CS_SKY_LUT_W * CS_SKY_LUT_H * 4;
+                r = ctx_build_sky_lut_into(c, q.light_direction, lut);
+                if (r) return r;
+                r = make_launch(c, &q, 0, 0, c->W, c->H, (uint16_t*)out + (size_t)i * image_px * 4, lut, L);
+                if (r) return r;
+                L.frame_consts = c->d_frame_consts + (size_t)s * (sizeof(FrameConsts) / sizeof(float));
+                launch_clouds_prologue(L, false, c->stream);
+            }
+            L.frame_consts = c->d_frame_consts;
+            L.n_suns = k; L.sun_stride_px = image_px;
+            if (!launch_clouds_fast_sunbatch(L, c->stream)) return fail(c, CS_ERR_INVALID, "cs_render_sun_batch_to: no batch kernel for this configuration");
+            CU(cudaGetLastError());
+        }
+        i += k;
     }
     return CS_OK;
 }

@@ -37,7 +37,9 @@ struct cs_context {
     uint16_t* d_sky = nullptr;
     bool have_tlut = false, have_sky = false;
     int tlut_param = CS_TLUT_LINEAR;  // cs_set_transmittance_parametrisation
-    float* d_frame_consts = nullptr;
+    float* d_frame_consts = nullptr;     // kMaxSunBatch x FrameConsts (a single frame uses the first)
+    uint16_t* d_sky_batch = nullptr;     // kMaxSunBatch sky LUTs for cs_render_sun_batch_to
+    bool sun_batching = true;            // CLOUDSKY_SUN_BATCH=0 in the environment: one launch per sun (A/B runs)
 
     // output
     int W = 0, H = 0;

@@ -12,6 +12,7 @@ namespace cs {
 
 constexpr int kMaxLargeLevels = 8;  // 128 -> 1
 constexpr int kMaxSmallLevels = 6;  // 32 -> 1
+constexpr int kMaxSunBatch = 4;     // suns marched together by the sun-batch kernel (cs_render_sun_batch_to)
 
 // ---- host-side assets (assets.cpp) ----------------------------------------------------------
 struct HostImage {
@@ -61,6 +62,8 @@ struct CloudLaunch {
     const float* frame_consts;                  // FrameConsts written by the prologue kernel
     uint16_t* out;                              // half4 image
     unsigned long long* counters;               // 6 x u64 or nullptr
+    int n_suns;                                 // sun-batch kernel: frame_consts holds this many FrameConsts, out this many images
+    size_t sun_stride_px;                       // pixels between consecutive images of a sun batch
     float band_lo, band_hi;                     // density() is exactly 0 for height fractions outside (band_lo, band_hi) (context.cu: height_band)
     unsigned int* tickets;                      // persistent-warp variant of the fast kernel: one patch-ticket counter per SM slot (zeroed by the launcher)
     int sm_slots;                               // number of SMs of the device
@@ -83,6 +86,7 @@ void launch_sky_lut(const uint16_t* transmittance_half4, int parametrisation, co
 void launch_clouds_prologue(const CloudLaunch& L, bool strict, void* stream);
 void launch_clouds_strict(const CloudLaunch& L, void* stream);
 void launch_clouds_fast(const CloudLaunch& L, void* stream);
+bool launch_clouds_fast_sunbatch(const CloudLaunch& L, void* stream);  // false: this configuration has no batch kernel
 void launch_noise(int kind, int n, const cs_noise_params& P, uint32_t* out_rgba8, void* stream);  // noise_gen.cu
 
 }  // namespace cs
