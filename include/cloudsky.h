@@ -260,7 +260,9 @@ int cs_render_frame_host(cs_context* ctx, const cs_cloud_params* params, uint16_
 int cs_render_frame_host_async(cs_context* ctx, const cs_cloud_params* params, uint16_t* out_half4, size_t out_bytes);
 int cs_wait_host(cs_context* ctx);
 /* Sun-angle batch (BASELINE config 4): for each of n suns build its sky LUT and render one full
- * frame into device_out_half4 + i*W*H*4 halfs.  Other params are shared. */
+ * frame into device_out_half4 + i*W*H*4 halfs.  Other params are shared.  In CS_MODE_FAST (no flags, counters and kernel
+ * timing off) up to 4 suns are marched per launch: everything a primary step computes before its light march is
+ * sun-independent and is computed once; every image is bit-identical to a single-sun cs_render_frame for that sun. */
 int cs_render_sun_batch_to(cs_context* ctx, const cs_cloud_params* params, const float* sun_dirs_xyz,
                            int n_suns, void* device_out_half4);
 /* Device-side timing of `iters` back-to-back full-frame dispatches with CUDA events on the

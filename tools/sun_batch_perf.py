@@ -14,6 +14,7 @@ W, H, P, cone, N = 2048, 1024, 128, 7, 8
 th = np.pi * (np.arange(N) + 0.5) / N
 suns = np.stack([np.cos(th), np.sin(th), np.zeros(N)], 1).astype(np.float32)  # dir_k = (cos, sin, 0)
 out = torch.zeros((N, H, W, 4), dtype=torch.float16, device="cuda")
+stream = torch.cuda.Stream()  # not the default stream: cs_set_stream(NULL) would mean "the context's own stream"
 ref = None
 for cov in (0.2, 1.0):
     for batched in ("1", "0"):
@@ -24,11 +25,11 @@ for cov in (0.2, 1.0):
         st = lib.frame_state_init(); lib.frame_advance(st, s, 1.0)
         p = lib.fill_cloud_params(s, st, W, H)
         ctx.set_march_config(P, cone, cs.MODE_FAST)
-        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        ctx.set_stream(stream.cuda_stream)
         best = 1e9
         for it in range(4):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(); ctx.render_sun_batch_to(p, suns, out.data_ptr()); e1.record(); torch.cuda.synchronize()
+            e0.record(stream); ctx.render_sun_batch_to(p, suns, out.data_ptr()); e1.record(stream); torch.cuda.synchronize()
             if it: best = min(best, e0.elapsed_time(e1))
         img = out.cpu().numpy()
         same = None if batched == "1" else bool((img.view(np.uint16) == ref.view(np.uint16)).all())
