@@ -271,12 +271,6 @@ int upload_levels(cs_context* c, const std::vector<uint8_t>& large0, int ln, con
     c->weather_w = ww; c->weather_h = wh;
     c->weather_type_hi = 1;
     for (size_t i = 0; i < weather.size(); i += 4) if (weather[i] < 128) { c->weather_type_hi = 0; break; }
-    c->weather_type_min = 255; c->weather_type_max = 0; c->weather_cov_max = 0;  // for the exact height band (height_band below)
-    for (size_t i = 0; i < weather.size(); i += 4) {
-        c->weather_type_min = std::min<int>(c->weather_type_min, weather[i]); c->weather_type_max = std::max<int>(c->weather_type_max, weather[i]);
-        c->weather_cov_max = std::max<int>(c->weather_cov_max, weather[i + 2]);
-    }
-    c->band_coverage = -1.0f;  // recompute on the next dispatch
     for (int l = 0; l < c->large_levels; l++) {
         CU(cudaMalloc(&c->d_large[l], c->h_large[l].size()));
         CU(cudaMemcpy(c->d_large[l], c->h_large[l].data(), c->h_large[l].size(), cudaMemcpyHostToDevice));
@@ -319,38 +313,6 @@ int upload_levels(cs_context* c, const std::vector<uint8_t>& large0, int ln, con
     CU(make_weather_texture(weather, ww, wh, &c->a_weather, &c->t_weather));
     c->have_tex = true;
     return CS_OK;
-}
-
-// The height band outside of which density() (clouds.glsl:109-137) is exactly 0 for EVERY weather texel of the uploaded map:
-// density is 0 whenever max(g, 0) <= 1 - coverage * weather.b (the coverage remap cannot exceed 0 there), g depends only on the
-// height fraction and the cloud type, and linear filtering keeps type and coverage inside the texel range.  So with
-// G(h) = max over type in [type_min, type_max] of densityHeightGradient(h, type), every sample with G(h) <= 1 - coverage * b_max
-// is empty.  {h : G(h) > threshold} is an interval (each type's g rises, then falls); it is located on a fine grid in double
-// precision and widened by two grid cells plus a threshold margin far above the kernel's fp32 / fast-division error, so the
-// kernel may skip the weather fetch and the gradient outside (band_lo, band_hi) without changing a single bit of the image.
-void height_band(const cs_context* c, float coverage, float* lo, float* hi) {
-    const double tmin = c->weather_type_min / 255.0, tmax = c->weather_type_max / 255.0;
-    const double threshold = 1.0 - (double)coverage * (c->weather_cov_max / 255.0) - 1e-3;
-    auto smooth = [](double e0, double e1, double x) { double t = std::min(std::max((x - e0) / (e1 - e0), 0.0), 1.0); return t * t * (3.0 - 2.0 * t); };
-    auto g = [&](double h, double type) {  // mixGradients + densityHeightGradient (clouds.glsl:82-95)
-        double st = 1.0 - std::min(std::max(type * 2.0, 0.0), 1.0), sc = 1.0 - std::fabs(type - 0.5) * 2.0, cu = std::min(std::max(type - 0.5, 0.0), 1.0) * 2.0;
-        double x = 0.02 * st + 0.02 * sc + 0.01 * cu, y = 0.05 * st + 0.2 * sc + 0.0625 * cu, z = 0.09 * st + 0.48 * sc + 0.78 * cu, w = 0.11 * st + 0.625 * sc + 1.0 * cu;
-        return smooth(x, y, h) - smooth(z, w, h);
-    };
-    const int N = 2048, T = 32;
-    int first = N + 1, last = -1;
-    for (int i = 0; i <= N; i++) {
-        double h = (double)i / N, best = -1.0;
-        for (int k = 0; k <= T; k++) best = std::max(best, g(h, tmin + (tmax - tmin) * k / T));
-        // g is Lipschitz in h (slope <= 1.5 / 0.0125 = 120 per unit) and in type: one grid cell changes it by < 0.06, two cells of
-        // widening plus the type grid are covered by also testing against a lowered threshold
-        if (best > threshold - 0.15) { first = std::min(first, i); last = std::max(last, i); }
-    }
-    if (last < 0) { *lo = 2.0f; *hi = -1.0f; return; }  // nothing can be cloud: every sample is skipped
-    *lo = (float)std::max(0.0, (double)(first - 2) / N) - 1e-6f;
-    *hi = (float)std::min(1.0, (double)(last + 2) / N) + 1e-6f;
-    if (first <= 2) *lo = -1.0f;  // the band reaches the slab floor / top: the clamped height fractions 0 and 1 stay inside
-    if (last >= N - 2) *hi = 2.0f;
 }
 
 int make_launch(cs_context* c, const cs_cloud_params* P, int x0, int y0, int x1, int y1, uint16_t* out, const uint16_t* sky_lut, CloudLaunch& L) {
@@ -397,11 +359,7 @@ int make_launch(cs_context* c, const cs_cloud_params* P, int x0, int y0, int x1,
     L.frame_consts = c->d_frame_consts;
     L.out = out;
     L.counters = c->counters_on ? c->d_counters : nullptr;
-    if (c->band_coverage != P->cloud_coverage) { height_band(c, P->cloud_coverage, &c->band_lo, &c->band_hi); c->band_coverage = P->cloud_coverage; }
-    L.band_lo = c->band_lo; L.band_hi = c->band_hi;
     L.n_suns = 1; L.sun_stride_px = 0;
-    L.tickets = c->d_tickets;
-    L.sm_slots = c->sm_count;
     return CS_OK;
 }
 
@@ -473,9 +431,7 @@ int cs_create(int device, cs_context** out) {
               cudaMalloc(&c->d_sky, (size_t)CS_SKY_LUT_W * CS_SKY_LUT_H * 8) == cudaSuccess &&
               cudaMalloc(&c->d_frame_consts, sizeof(FrameConsts) * kMaxSunBatch) == cudaSuccess &&
               cudaMalloc(&c->d_sky_batch, (size_t)CS_SKY_LUT_W * CS_SKY_LUT_H * 8 * kMaxSunBatch) == cudaSuccess &&
-              cudaMalloc(&c->d_counters, 6 * sizeof(unsigned long long)) == cudaSuccess &&
-              cudaMalloc(&c->d_tickets, 1024 * sizeof(unsigned int)) == cudaSuccess &&
-              cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && c->sm_count > 0 && c->sm_count <= 1024;
+              cudaMalloc(&c->d_counters, 6 * sizeof(unsigned long long)) == cudaSuccess;
     if (!ok) {
         fprintf(stderr, "cloudsky_b200: cs_create: %s\n", cudaGetErrorString(cudaGetLastError()));
         cs_destroy(c);
@@ -496,7 +452,6 @@ void cs_destroy(cs_context* c) {
     if (c->d_sky) cudaFree(c->d_sky);
     if (c->d_frame_consts) cudaFree(c->d_frame_consts);
     if (c->d_counters) cudaFree(c->d_counters);
-    if (c->d_tickets) cudaFree(c->d_tickets);
     if (c->d_sky_batch) cudaFree(c->d_sky_batch);
     if (c->d_image) cudaFree(c->d_image);
     for (auto e : c->ev_march) cudaEventDestroy(e);

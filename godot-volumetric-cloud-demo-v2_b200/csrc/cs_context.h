@@ -17,8 +17,6 @@ struct cs_context {
     bool have_tex = false;
     int large_n = 0, large_levels = 0, small_n = 0, small_levels = 0, weather_w = 0, weather_h = 0;
     int weather_type_hi = 0;
-    int weather_type_min = 0, weather_type_max = 255, weather_cov_max = 255;  // texel ranges of the weather map (R, B)
-    float band_coverage = -1.0f, band_lo = -1.0f, band_hi = 2.0f;              // cached exact height band for this cloud_coverage
     int records_half = 0;  // 1: d_*_f hold exact-integer fp16 records, 0: fp32 records
     uint32_t* d_large[cs::kMaxLargeLevels] = {};
     uint32_t* d_small[cs::kMaxSmallLevels] = {};
@@ -55,8 +53,6 @@ struct cs_context {
     int primary_steps = CS_REF_PRIMARY_STEPS, cone_samples = CS_REF_CONE_SAMPLES, mode = CS_MODE_FAST;
     bool counters_on = false;
     unsigned long long* d_counters = nullptr;
-    unsigned int* d_tickets = nullptr;  // per-SM patch tickets (persistent-warp variant of the fast kernel)
-    int sm_count = 0;
 
     // optional per-kernel event timing (cs_set_kernel_timing)
     bool timing_on = false;

@@ -64,9 +64,6 @@ struct CloudLaunch {
     unsigned long long* counters;               // 6 x u64 or nullptr
     int n_suns;                                 // sun-batch kernel: frame_consts holds this many FrameConsts, out this many images
     size_t sun_stride_px;                       // pixels between consecutive images of a sun batch
-    float band_lo, band_hi;                     // density() is exactly 0 for height fractions outside (band_lo, band_hi) (context.cu: height_band)
-    unsigned int* tickets;                      // persistent-warp variant of the fast kernel: one patch-ticket counter per SM slot (zeroed by the launcher)
-    int sm_slots;                               // number of SMs of the device
 };
 
 // Pixel-independent values of march()'s prologue (clouds.glsl:149-167), computed once per

@@ -1,6 +1,7 @@
 #!/bin/bash
 # Development aid: build launch-shape / knob variants of the fast kernel into build/variants/lib_<name>.so.
 # usage: tools/build_variants.sh name1:"-DCS_X=1 -DCS_Y=2" name2:"..."   (then: python tools/shape_sweep.py [--flags N])
+# e.g.   tools/build_variants.sh scalar:"-DCS_PACKED_F32=0" rec9:"-DCS_REC_MIN_BLOCKS=9" thr20:"-DCS_DIRECT_THRESHOLD=20"
 set -e
 cd "$(dirname "$0")/../godot-volumetric-cloud-demo-v2_b200/csrc"
 make -s >/dev/null
