@@ -59,10 +59,6 @@ void free_textures(cs_context* c) {
     if (c->a_large) cudaFreeMipmappedArray(c->a_large);
     if (c->a_small) cudaFreeMipmappedArray(c->a_small);
     if (c->a_weather) cudaFreeArray(c->a_weather);
-    for (auto& t : c->t_large2) { if (t) cudaDestroyTextureObject(t); t = 0; }
-    for (auto& t : c->t_small2) { if (t) cudaDestroyTextureObject(t); t = 0; }
-    for (auto& a : c->a_large2) { if (a) cudaFreeArray(a); a = nullptr; }
-    for (auto& a : c->a_small2) { if (a) cudaFreeArray(a); a = nullptr; }
     c->t_large = c->t_small = c->t_weather = 0;
     c->a_large = c->a_small = nullptr; c->a_weather = nullptr;
     c->have_tex = false;
@@ -103,47 +99,6 @@ cudaError_t make_weather_texture(const std::vector<uint8_t>& rgba, int w, int h,
     cudaError_t e = cudaMallocArray(arr, &fd, w, h, 0);
     if (e != cudaSuccess) return e;
     if ((e = cudaMemcpy2DToArray(*arr, 0, 0, rgba.data(), (size_t)w * 4, (size_t)w * 4, h, cudaMemcpyHostToDevice)) != cudaSuccess) return e;
-    cudaResourceDesc rd = {};
-    rd.resType = cudaResourceTypeArray;
-    rd.res.array.array = *arr;
-    cudaTextureDesc td = {};
-    td.addressMode[0] = td.addressMode[1] = cudaAddressModeWrap;
-    td.filterMode = cudaFilterModeLinear;
-    td.readMode = cudaReadModeNormalizedFloat;
-    td.normalizedCoords = 1;
-    return cudaCreateTextureObject(tex, &rd, &td, nullptr);
-}
-
-// CS_MODE_TEX, two-slice layered form of one mip level of a volume: layer z of an n x n x n-layer 2-D array holds, per texel,
-// the values the shader needs from slices z and z+1 (REPEAT wrap baked in) as unorm16 — large volume: (R(z), R(z+1), K(z), K(z+1))
-// with R * 257 and K * 32 (K = 5G+2B+A <= 2040), small volume: (h(z), h(z+1)) with h = 5R+2G+B times 32 — all exact.  One
-// bilinear fetch of layer floor(z) then yields both slices; the kernel lerps them in fp32 (clouds_fast.cu: sample_large/small).
-cudaError_t make_two_slice_texture(const std::vector<uint8_t>& rgba, int n, bool large, cudaArray_t* arr, cudaTextureObject_t* tex) {
-    const int ch = large ? 4 : 2;
-    std::vector<uint16_t> t((size_t)n * n * n * ch);
-    for (int z = 0; z < n; z++) {
-        const int z1 = (z + 1) % n;
-        for (size_t i = 0; i < (size_t)n * n; i++) {
-            const uint8_t* a = &rgba[((size_t)z * n * n + i) * 4];
-            const uint8_t* b = &rgba[((size_t)z1 * n * n + i) * 4];
-            uint16_t* o = &t[((size_t)z * n * n + i) * ch];
-            if (large) {
-                o[0] = (uint16_t)(a[0] * 257); o[1] = (uint16_t)(b[0] * 257);
-                o[2] = (uint16_t)((5 * a[1] + 2 * a[2] + a[3]) * 32); o[3] = (uint16_t)((5 * b[1] + 2 * b[2] + b[3]) * 32);
-            } else {
-                o[0] = (uint16_t)((5 * a[0] + 2 * a[1] + a[2]) * 32); o[1] = (uint16_t)((5 * b[0] + 2 * b[1] + b[2]) * 32);
-            }
-        }
-    }
-    cudaChannelFormatDesc fd = large ? cudaCreateChannelDesc<ushort4>() : cudaCreateChannelDesc<ushort2>();
-    cudaError_t e = cudaMalloc3DArray(arr, &fd, make_cudaExtent(n, n, n), cudaArrayLayered);
-    if (e != cudaSuccess) return e;
-    cudaMemcpy3DParms cp = {};
-    cp.srcPtr = make_cudaPitchedPtr(t.data(), (size_t)n * ch * 2, n, n);
-    cp.dstArray = *arr;
-    cp.extent = make_cudaExtent(n, n, n);
-    cp.kind = cudaMemcpyHostToDevice;
-    if ((e = cudaMemcpy3D(&cp)) != cudaSuccess) return e;
     cudaResourceDesc rd = {};
     rd.resType = cudaResourceTypeArray;
     rd.res.array.array = *arr;
@@ -356,8 +311,6 @@ int upload_levels(cs_context* c, const std::vector<uint8_t>& large0, int ln, con
     CU(make_volume_texture(c->h_large, ln, &c->a_large, &c->t_large));
     CU(make_volume_texture(c->h_small, sn, &c->a_small, &c->t_small));
     CU(make_weather_texture(weather, ww, wh, &c->a_weather, &c->t_weather));
-    for (int l = 0; l < c->large_levels; l++) CU(make_two_slice_texture(c->h_large[l], ln >> l, true, &c->a_large2[l], &c->t_large2[l]));
-    for (int l = 0; l < c->small_levels; l++) CU(make_two_slice_texture(c->h_small[l], sn >> l, false, &c->a_small2[l], &c->t_small2[l]));
     c->have_tex = true;
     return CS_OK;
 }
@@ -396,16 +349,12 @@ int make_launch(cs_context* c, const cs_cloud_params* P, int x0, int y0, int x1,
     if ((c->small_n >> (c->small_levels - 1)) == 1) {
         const uint8_t* t = c->h_small[c->small_levels - 1].data();
         L.small_tail_level = c->small_levels - 1;
-        if ((c->mode & CS_MODE_TEX) && (c->tex_layered & 1)) L.small_tail_value = (float)(5 * t[0] + 2 * t[1] + t[2]) * (1.0f / 2040.0f);
-        else if (c->mode & CS_MODE_TEX) L.small_tail_value = fmaf(un8(t[0]), 0.625f, fmaf(un8(t[1]), 0.25f, un8(t[2]) * 0.125f));
+        if (c->mode & CS_MODE_TEX) L.small_tail_value = fmaf(un8(t[0]), 0.625f, fmaf(un8(t[1]), 0.25f, un8(t[2]) * 0.125f));
         else if (c->records_half & 2) L.small_tail_value = (float)(5 * t[0] + 2 * t[1] + t[2]) * (1.0f / 2040.0f);
         else L.small_tail_value = un8(t[0]) * 0.625f + un8(t[1]) * 0.25f + un8(t[2]) * 0.125f;
     }
     L.tex_large = c->t_large; L.tex_small = c->t_small; L.tex_weather = c->t_weather;
     L.hw_filter = (c->mode & CS_MODE_TEX) ? 1 : 0;
-    for (int l = 0; l < kMaxLargeLevels; l++) L.tex_large2[l] = c->t_large2[l];
-    for (int l = 0; l < kMaxSmallLevels; l++) L.tex_small2[l] = c->t_small2[l];
-    L.tex_layered = c->tex_layered;
     L.sky_lut = sky_lut ? sky_lut : c->d_sky;
     L.frame_consts = c->d_frame_consts;
     L.out = out;
@@ -490,7 +439,6 @@ int cs_create(int device, cs_context** out) {
     }
     c->stream = c->own_stream;
     if (const char* e = getenv("CLOUDSKY_SUN_BATCH")) c->sun_batching = e[0] != '0';  // development knob: 0 = one launch per sun
-    if (const char* e = getenv("CLOUDSKY_TEX_LAYERED")) c->tex_layered = atoi(e) & 3;     // CS_MODE_TEX: bit 0 small, bit 1 large volume from the two-slice textures
     *out = c;
     return CS_OK;
 }

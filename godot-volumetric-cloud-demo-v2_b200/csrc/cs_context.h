@@ -28,10 +28,6 @@ struct cs_context {
     cudaMipmappedArray_t a_large = nullptr, a_small = nullptr;
     cudaArray_t a_weather = nullptr;
     cudaTextureObject_t t_large = 0, t_small = 0, t_weather = 0;
-    // ... and per mip level as layered two-slice textures (context.cu: make_two_slice_texture)
-    cudaArray_t a_large2[cs::kMaxLargeLevels] = {}, a_small2[cs::kMaxSmallLevels] = {};
-    cudaTextureObject_t t_large2[cs::kMaxLargeLevels] = {}, t_small2[cs::kMaxSmallLevels] = {};
-    int tex_layered = 0;  // which volumes CS_MODE_TEX fetches from them (bit 0 small, bit 1 large; CLOUDSKY_TEX_LAYERED)
     std::vector<std::vector<uint8_t>> h_large, h_small;  // host copies of the mip chains (readback / repack)
 
     // LUTs

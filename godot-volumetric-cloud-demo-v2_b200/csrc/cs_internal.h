@@ -58,9 +58,6 @@ struct CloudLaunch {
     // CS_MODE_TEX: texture objects over the same RGBA8 mip chains (REPEAT, linear, explicit level), filtered by the texture unit
     unsigned long long tex_large, tex_small, tex_weather;  // cudaTextureObject_t
     int hw_filter;                                          // 1: the fast kernel samples through the texture objects
-    // per-level layered two-slice textures of the volumes (CS_MODE_TEX; context.cu: make_two_slice_textures)
-    unsigned long long tex_large2[kMaxLargeLevels], tex_small2[kMaxSmallLevels];
-    int tex_layered;                                        // bit 0: small volume, bit 1: large volume fetched from the two-slice textures
     const uint16_t* sky_lut;                    // half4 200x100
     const float* frame_consts;                  // FrameConsts written by the prologue kernel
     uint16_t* out;                              // half4 image

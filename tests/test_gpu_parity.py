@@ -406,57 +406,6 @@ def test_render_frame_host_and_sun_batch(cs, pair, helpers, product_lib):
         assert (single.view(np.uint16) == batch[i].view(np.uint16)).all()
 
 
-@pytest.mark.parametrize("layered", [1, 2, 3])
-def test_texture_unit_two_slice_layered_volumes(cs, pair, helpers, product_lib, textures, small_textures, layered, monkeypatch):
-    """CS_MODE_TEX with the volumes bound as two-slice layered textures (CLOUDSKY_TEX_LAYERED, read at cs_create: bit 0 small,
-    bit 1 large volume): one bilinear fetch per sample instead of a 3-D trilinear one, z lerped in fp32 in the kernel.  Same
-    parity gate against the oracle as every FAST mode; close to the 3-D texture path; works with small odd volumes, with more
-    light samples than the cooperative tables hold, and with the early-out flag."""
-    o, g0, W, H = pair
-    p = helpers.make_params(product_lib, W, H, time=3.0)
-    o.set_march_config(128, 6); o.build_sky_lut(tuple(p.light_direction)); o.render_frame(p)
-    ref = o.read_image()
-    g0.write_sky_lut(o.read_sky_lut())
-    g0.set_march_config(128, 6, cs.MODE_FAST | cs.MODE_TEX); g0.render_frame(p)
-    tex3d = g0.read_image()
-    g0.set_march_config(128, 6, cs.MODE_FAST)
-    monkeypatch.setenv("CLOUDSKY_TEX_LAYERED", str(layered))
-    g = helpers.prepared_context(product_lib, textures, W, H)
-    g.write_sky_lut(o.read_sky_lut())
-    g.set_march_config(128, 6, cs.MODE_FAST | cs.MODE_TEX); g.render_frame(p)
-    img = g.read_image()
-    assert np.isfinite(img.astype(np.float32)).all()
-    assert not (img.view(np.uint16) == tex3d.view(np.uint16)).all()          # a different fetch path (fp32 z weight)
-    frac, mx = helpers.compare_images(img, ref, 2e-3, 1e-2)
-    assert frac >= 0.999 and mx < 0.1, (layered, frac, mx)                    # the FAST gate against the oracle
-    frac, mx = helpers.compare_images(img, tex3d, 2e-3, 1e-2)
-    assert frac >= 0.9995 and mx < 0.02, (layered, frac, mx)
-    g.set_march_config(128, 6, cs.MODE_FAST | cs.MODE_TEX | cs.MODE_EARLY_OUT); g.render_frame(p)
-    early = g.read_image()
-    assert (early[..., 3].view(np.uint16) == img[..., 3].view(np.uint16)).all()
-    o.set_march_config(128, 20); o.render_frame(p)                            # sequential light walk (> 16 samples)
-    g.set_march_config(128, 20, cs.MODE_FAST | cs.MODE_TEX); g.render_frame(p)
-    frac, mx = helpers.compare_images(g.read_image(), o.read_image(), 2e-3, 1e-2)
-    assert frac >= 0.998, (layered, frac, mx)
-    o.set_march_config(128, 6)
-    g.close()
-    # small random volumes (16^3 / 8^3: every mip level down to 1^3 is exercised by the light samples), all cloud types
-    gs = helpers.prepared_context(product_lib, small_textures, 96, 48)
-    gs.set_march_config(48, 6, cs.MODE_FAST | cs.MODE_TEX)
-    q = helpers.make_params(product_lib, 96, 48, coverage=0.6)
-    gs.render_frame(q)
-    a = gs.read_image()
-    gs.close()
-    monkeypatch.setenv("CLOUDSKY_TEX_LAYERED", "0")
-    gs = helpers.prepared_context(product_lib, small_textures, 96, 48)
-    gs.set_march_config(48, 6, cs.MODE_FAST | cs.MODE_TEX)
-    gs.render_frame(q)
-    b = gs.read_image()
-    gs.close()
-    frac, mx = helpers.compare_images(a, b, 2e-3, 1e-2)
-    assert frac >= 0.995 and mx < 0.1, (layered, frac, mx)                    # random texels: every filter difference is amplified
-
-
 @pytest.mark.parametrize("which", ["reference_textures", "fp32_records"])
 def test_sun_batch_kernel_matches_single_launches(cs, product_lib, textures, small_textures, helpers, which, monkeypatch):
     """cs_render_sun_batch_to marches up to 4 suns per launch (the primary loop is sun-independent); every image must be the
