@@ -28,6 +28,18 @@ def row_bands(height: int, world: int) -> List[Tuple[int, int]]:
     return [(r * rows, (r + 1) * rows) for r in range(world)]
 
 
+def interleaved_bands(height: int, world: int, bands_per_rank: int) -> List[List[Tuple[int, int]]]:
+    """Row bands for a frame whose cost varies with the row (the lit fraction does): the image is cut into
+    world * bands_per_rank equal bands and rank r takes bands r, r + world, r + 2 world, ...  Band group g (bands g*world ..
+    g*world + world - 1) is a contiguous block of `world` equal chunks in rank order, so it is gathered by one in-place
+    all-gather.  Returns, per rank, its bands_per_rank (r0, r1) ranges in group order."""
+    n = world * bands_per_rank
+    if world < 1 or bands_per_rank < 1 or height % n != 0:
+        raise ValueError(f"height {height} is not divisible by {world} ranks x {bands_per_rank} bands")
+    rows = height // n
+    return [[((g * world + r) * rows, (g * world + r + 1) * rows) for g in range(bands_per_rank)] for r in range(world)]
+
+
 def sun_sweep(n: int) -> np.ndarray:
     """BASELINE config 4 / SURVEY §8(d) C4: dir_k = (cos th_k, sin th_k, 0), th_k = pi (k + 0.5) / n."""
     th = math.pi * (np.arange(n, dtype=np.float64) + 0.5) / n
@@ -64,18 +76,23 @@ class ShardedRenderer:
         if ctx.width != width or ctx.height != height:
             ctx.resize(width, height)
 
-    def render_frame_rows(self, params):
-        """One frame split into row bands; returns the gathered [H, W, 4] fp16 tensor (identical on all ranks)."""
+    def render_frame_rows(self, params, bands_per_rank: int = 1):
+        """One frame split into row bands; returns the gathered [H, W, 4] fp16 tensor (identical on all ranks).
+        bands_per_rank > 1 interleaves the bands over the ranks (interleaved_bands) to even out the lit fraction; the result is
+        the same texture, gathered with one all-gather per band group."""
         torch = self.torch
         full = torch.zeros((self.H, self.W, 4), dtype=torch.float16, device=self.device)
-        r0, r1 = row_bands(self.H, self.world)[self.rank]
-        self.ctx.render_rows_to(params, r0, r1, full.data_ptr())
+        mine = interleaved_bands(self.H, self.world, bands_per_rank)[self.rank]
+        for r0, r1 in mine:
+            self.ctx.render_rows_to(params, r0, r1, full.data_ptr())
         if self.device != "cpu":
             self.ctx.sync() if self._own_stream() else None
         if self.world > 1:
             flat = full.view(-1)
-            per = (r1 - r0) * self.W * 4
-            _all_gather_inplace(flat, flat[self.rank * per:(self.rank + 1) * per], self.group)
+            per = (mine[0][1] - mine[0][0]) * self.W * 4          # elements of one band
+            for g, (r0, _) in enumerate(mine):
+                group_flat = flat[g * self.world * per:(g + 1) * self.world * per]
+                _all_gather_inplace(group_flat, group_flat[self.rank * per:(self.rank + 1) * per], self.group)
         return full
 
     def render_sun_sweep(self, params, suns: Sequence[Sequence[float]]):

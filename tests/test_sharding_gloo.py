@@ -17,6 +17,12 @@ def test_partition_helpers(cs):
     assert sharding.row_bands(64, 1) == [(0, 64)]
     with pytest.raises(ValueError):
         sharding.row_bands(100, 8)
+    assert sharding.interleaved_bands(64, 2, 1) == [[(0, 32)], [(32, 64)]]
+    assert sharding.interleaved_bands(64, 2, 2) == [[(0, 16), (32, 48)], [(16, 32), (48, 64)]]
+    bands = sharding.interleaved_bands(1024, 8, 4)
+    assert sorted(b for r in bands for b in r) == [(32 * i, 32 * (i + 1)) for i in range(32)]   # a partition of the rows
+    with pytest.raises(ValueError):
+        sharding.interleaved_bands(100, 2, 3)
     s = sharding.sun_sweep(64)
     assert s.shape == (64, 3) and np.allclose(np.linalg.norm(s, axis=1), 1.0, atol=1e-6)
     assert s[0, 0] > 0.99 and s[-1, 0] < -0.99 and (s[:, 1] > 0).all() and (s[:, 2] == 0).all()
@@ -44,6 +50,8 @@ def _worker(rank, world, port, out_dir):
     r = sharding.ShardedRenderer(ctx, W, H, device="cpu")
     assert (r.world, r.rank) == (world, rank)
     frame = r.render_frame_rows(p).numpy()
+    inter = r.render_frame_rows(p, bands_per_rank=4).numpy()  # interleaved bands, one all-gather per band group
+    assert (inter.view(np.uint16) == frame.view(np.uint16)).all()
     sweep = r.render_sun_sweep(p, sharding.sun_sweep(4)).numpy()
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), frame=frame, sweep=sweep)
     dist.barrier()
