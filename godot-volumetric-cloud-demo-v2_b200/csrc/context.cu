@@ -770,7 +770,7 @@ int cs_render_sun_batch_to(cs_context* c, const cs_cloud_params* P, const float*
     const size_t image_px = (size_t)c->W * c->H;
     // CS_MODE_FAST with the record sampler: up to kMaxSunBatch suns share one march (clouds_fast_sunbatch_kernel) — the primary
     // loop is sun-independent.  Other modes, instrumented runs and step counts beyond the tables: one launch per sun.
-    const bool batched = (c->mode == CS_MODE_FAST || c->mode == (CS_MODE_FAST | CS_MODE_TEX)) && !c->counters_on && !c->timing_on && c->cone_samples + 1 <= 16 && n > 1 && c->have_tlut && c->sun_batching;
+    const bool batched = c->mode == CS_MODE_FAST && !c->counters_on && !c->timing_on && c->cone_samples + 1 <= 16 && n > 1 && c->have_tlut && c->sun_batching;
     int i = 0;
     while (i < n) {
         const int k = batched ? std::min(n - i, (int)kMaxSunBatch) : 1;

@@ -406,23 +406,21 @@ def test_render_frame_host_and_sun_batch(cs, pair, helpers, product_lib):
         assert (single.view(np.uint16) == batch[i].view(np.uint16)).all()
 
 
-@pytest.mark.parametrize("sampler", ["records", "texture_unit"])
 @pytest.mark.parametrize("which", ["reference_textures", "fp32_records"])
-def test_sun_batch_kernel_matches_single_launches(cs, product_lib, textures, small_textures, helpers, which, sampler, monkeypatch):
+def test_sun_batch_kernel_matches_single_launches(cs, product_lib, textures, small_textures, helpers, which, monkeypatch):
     """cs_render_sun_batch_to marches up to 4 suns per launch (the primary loop is sun-independent); every image must be the
     one a single-sun dispatch produces, bit for bit — chunks of 4 + 3, both lit-lane paths (coverage 0.2 and 1.0), an image
     whose size is not a multiple of the CTA tile, and both record formats."""
     import torch
     tex = textures if which == "reference_textures" else small_textures
     W, H = (200, 100) if which == "reference_textures" else (72, 40)
-    mode = cs.MODE_FAST | (cs.MODE_TEX if sampler == "texture_unit" else 0)
     th = np.linspace(0.15, 2.9, 7)
     suns = np.stack([np.cos(th), np.sin(th), 0.2 * np.cos(3 * th)], 1)
     suns = (suns / np.linalg.norm(suns, axis=1, keepdims=True)).astype(np.float32)
     for cov in (0.2, 1.0):
         p = helpers.make_params(product_lib, W, H, coverage=cov, time=4.0, wind_direction=0.4)
         g = helpers.prepared_context(product_lib, tex, W, H)
-        g.set_march_config(64, 6, mode)
+        g.set_march_config(64, 6, cs.MODE_FAST)
         out = torch.zeros((7, H, W, 4), dtype=torch.float16, device="cuda")
         g.set_stream(torch.cuda.current_stream().cuda_stream)
         g.render_sun_batch_to(p, suns, out.data_ptr())
@@ -440,7 +438,7 @@ def test_sun_batch_kernel_matches_single_launches(cs, product_lib, textures, sma
     # the per-sun fallback (CLOUDSKY_SUN_BATCH=0, read at cs_create) gives the same bits
     monkeypatch.setenv("CLOUDSKY_SUN_BATCH", "0")
     g = helpers.prepared_context(product_lib, tex, W, H)
-    g.set_march_config(64, 6, mode)
+    g.set_march_config(64, 6, cs.MODE_FAST)
     out2 = torch.zeros((7, H, W, 4), dtype=torch.float16, device="cuda")
     g.set_stream(torch.cuda.current_stream().cuda_stream)
     g.render_sun_batch_to(p, suns, out2.data_ptr())
