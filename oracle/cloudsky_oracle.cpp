@@ -6,14 +6,14 @@
  * bench.py's cpu_baseline / --impl reference legs).  Nothing in the product path may link,
  * import or call this file.
  *
- * PARITY UNPINNED: the reference (clayjohn/godot-volumetric-cloud-demo-v2 @ 7c38fd9) ships no
- * tests, golden vectors or fixtures, and nothing in the build container can execute Godot /
- * Vulkan / GLSL, so this restatement cannot be checked against outputs of the reference itself.
- * It is pinned only by analytic known-answer tests derived from the shader source
- * (tests/test_oracle_*.py).  Third-party arithmetic outside the reference tree (Godot Engine
- * "4.2 or later", un-vendored): BC7 compression of the inputs, Godot's mip generator, driver
- * pow/exp/atan/asin and hardware 8-bit filter weights are NOT reproduced; the oracle samples
- * the raw 8-bit texels with fp32 weights and 2x2x2 box-filter mips re-quantised to 8 bits.
+ * PARITY PINNED (round 2): the reference ships no tests, golden vectors or fixtures, and nothing here can run Godot /
+ * Vulkan, but its three GLSL compute shaders compile UNMODIFIED as C++ behind oracle/glsl_compat.h (oracle/build_ref.sh
+ * -> oracle/_ref/libcloudsky_ref.so).  This restatement is bit-identical to that compiled reference: both LUTs on every
+ * texel and the cloud image on every pixel, 5 parameter sets (tests/test_reference_pin.py), and to the vectors the
+ * compiled reference produced (tests/golden/ref_golden.npz).  What stays unpinned is third-party arithmetic outside the
+ * reference tree (Godot Engine "4.2 or later", un-vendored): BC7 compression of the inputs, Godot's mip generator, a GPU
+ * driver's pow/exp/atan/asin and the texture unit's 8-bit filter weights; the oracle (like _ref) samples the raw 8-bit
+ * texels with fp32 weights and 2x2x2 box-filter mips re-quantised to 8 bits.
  *
  * Rules of the restatement: fp32 throughout, GLSL operation order, built with
  * -O2 -ffp-contract=off (no FMA contraction), round-to-nearest-even fp16 at every RGBA16F
