@@ -320,9 +320,12 @@ class Context:
         if r != CS_OK or not self._h:
             raise CloudSkyError(r, f"cs_create(device={device}) failed on backend {lib.backend}")
         self.width = self.height = 0
+        self._skies = []  # Sky objects created on this context
 
     def close(self) -> None:
         if getattr(self, "_h", None):
+            for sky in list(getattr(self, "_skies", [])):
+                sky.close()
             self.lib.dll.cs_destroy(self._h)
             self._h = None
 
@@ -485,20 +488,17 @@ class Sky:
         self.ctx = ctx
         self._h = _P()
         ctx._ck(ctx.lib.dll.cs_sky_create(ctx._h, C.byref(settings), C.byref(self._h)))
-        self._sync_size()
-
-    def _sync_size(self) -> None:
-        n = self.frame().texture_size  # the library resizes the context's image with the sky (update_performance)
-        self.ctx.width = self.ctx.height = n
+        ctx._skies.append(self)  # Context.close() destroys its skies first (a cs_sky keeps a pointer to its context)
 
     def close(self) -> None:
         if getattr(self, "_h", None):
             self.ctx.lib.dll.cs_sky_destroy(self._h)
             self._h = None
+            if self in self.ctx._skies:
+                self.ctx._skies.remove(self)
 
     def set_settings(self, settings: SkySettings) -> None:
         self.ctx._ck(self.ctx.lib.dll.cs_sky_set_settings(self._h, C.byref(settings)))
-        self._sync_size()
 
     def set_sun(self, basis_columns, energy: float, color_srgb) -> None:
         b = (C.c_float * 9)(*[float(v) for v in basis_columns])

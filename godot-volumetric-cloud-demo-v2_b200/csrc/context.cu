@@ -315,18 +315,21 @@ int upload_levels(cs_context* c, const std::vector<uint8_t>& large0, int ln, con
     return CS_OK;
 }
 
-int make_launch(cs_context* c, const cs_cloud_params* P, int x0, int y0, int x1, int y1, uint16_t* out, const uint16_t* sky_lut, CloudLaunch& L) {
+// img_w/img_h > 0: `out` is a caller-owned image of that size (a cs_sky's own textures); otherwise the context's image size.
+int make_launch(cs_context* c, const cs_cloud_params* P, int x0, int y0, int x1, int y1, uint16_t* out, const uint16_t* sky_lut, CloudLaunch& L,
+                int img_w = 0, int img_h = 0) {
+    const int IW = img_w > 0 ? img_w : c->W, IH = img_h > 0 ? img_h : c->H;
     if (!c->have_tex) return fail(c, CS_ERR_NOT_READY, "input textures not uploaded (can_run == false)");
     if (!sky_lut && !c->have_sky) return fail(c, CS_ERR_NOT_READY, "sky LUT not built (Attempting to render with an uninitialized sky lut)");
-    if (c->W < 1 || !out) return fail(c, CS_ERR_NOT_READY, "cs_resize not called");
-    if ((int)P->texture_size[0] != c->W || (int)P->texture_size[1] != c->H)
+    if (IW < 1 || !out) return fail(c, CS_ERR_NOT_READY, "cs_resize not called");
+    if ((int)P->texture_size[0] != IW || (int)P->texture_size[1] != IH)
         return fail(c, CS_ERR_INVALID, "params.texture_size does not match the image size set with cs_resize");
     std::memset(&L, 0, sizeof(L));
     L.P = *P;
-    L.width = c->W; L.height = c->H;
+    L.width = IW; L.height = IH;
     L.x0 = x0 < 0 ? 0 : x0; L.y0 = y0 < 0 ? 0 : y0;
-    L.x1 = x1 > c->W ? c->W : x1; L.y1 = y1 > c->H ? c->H : y1;
-    L.out_pitch_px = c->W;
+    L.x1 = x1 > IW ? IW : x1; L.y1 = y1 > IH ? IH : y1;
+    L.out_pitch_px = IW;
     L.primary_steps = c->primary_steps; L.cone_samples = c->cone_samples;
     // below 2^-12 the remaining radiance is < 1 fp16 ulp and alpha = 1 - T already rounds to 1.0 in fp16
     L.early_out_T = (c->mode & CS_MODE_EARLY_OUT) ? 0.000244140625f : 0.0f;
@@ -374,12 +377,13 @@ void timing_mark(cs_context* c, std::vector<cudaEvent_t>& evs, size_t pair, int 
 }
 
 // prologue + march for one rectangle, asynchronous on c->stream
-int dispatch(cs_context* c, const cs_cloud_params* P, int x0, int y0, int x1, int y1, uint16_t* out, const uint16_t* sky_lut = nullptr) {
+int dispatch(cs_context* c, const cs_cloud_params* P, int x0, int y0, int x1, int y1, uint16_t* out, const uint16_t* sky_lut = nullptr,
+             int img_w = 0, int img_h = 0) {
     if (!c || !P) return CS_ERR_INVALID;
     int r = bind(c);
     if (r) return r;
     CloudLaunch L;
-    r = make_launch(c, P, x0, y0, x1, y1, out, sky_lut, L);
+    r = make_launch(c, P, x0, y0, x1, y1, out, sky_lut, L, img_w, img_h);
     if (r) return r;
     if (L.x1 <= L.x0 || L.y1 <= L.y0) return CS_OK;
     if (L.counters) CU(cudaMemsetAsync(c->d_counters, 0, 6 * sizeof(unsigned long long), c->stream));
@@ -395,8 +399,8 @@ int dispatch(cs_context* c, const cs_cloud_params* P, int x0, int y0, int x1, in
 }  // namespace
 
 namespace cs {
-int ctx_dispatch(cs_context* c, const cs_cloud_params* P, int x0, int y0, int x1, int y1, uint16_t* out, const uint16_t* sky_lut) {
-    return dispatch(c, P, x0, y0, x1, y1, out, sky_lut);
+int ctx_dispatch(cs_context* c, const cs_cloud_params* P, int x0, int y0, int x1, int y1, uint16_t* out, const uint16_t* sky_lut, int img_w, int img_h) {
+    return dispatch(c, P, x0, y0, x1, y1, out, sky_lut, img_w, img_h);
 }
 int ctx_build_sky_lut_into(cs_context* c, const float sun[3], uint16_t* dst) {
     if (!c || !sun || !dst) return CS_ERR_INVALID;
@@ -447,6 +451,7 @@ void cs_destroy(cs_context* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);  // an in-flight device->host copy must not outlive its source image
     free_textures(c);
     if (c->d_tlut) cudaFree(c->d_tlut);
     if (c->d_sky) cudaFree(c->d_sky);
@@ -454,6 +459,12 @@ void cs_destroy(cs_context* c) {
     if (c->d_counters) cudaFree(c->d_counters);
     if (c->d_sky_batch) cudaFree(c->d_sky_batch);
     if (c->d_image) cudaFree(c->d_image);
+    if (c->d_image2) cudaFree(c->d_image2);
+    for (int i = 0; i < 2; i++) {
+        if (c->ev_rendered[i]) cudaEventDestroy(c->ev_rendered[i]);
+        if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
+    }
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     for (auto e : c->ev_march) cudaEventDestroy(e);
     for (auto e : c->ev_sky) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -810,11 +821,16 @@ int cs_time_render_frame(cs_context* c, const cs_cloud_params* P, int warmup, in
     int r = bind(c);
     if (r) return r;
     for (int i = 0; i < warmup; i++) { r = dispatch(c, P, 0, 0, c->W, c->H, c->d_image); if (r) return r; }
-    cudaEvent_t e0, e1;
-    CU(cudaEventCreate(&e0));
-    CU(cudaEventCreate(&e1));
-    CU(cudaStreamSynchronize(c->stream));
-    CU(cudaEventRecord(e0, c->stream));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaError_t ce = cudaEventCreate(&e0);
+    if (ce == cudaSuccess) ce = cudaEventCreate(&e1);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(c->stream);
+    if (ce == cudaSuccess) ce = cudaEventRecord(e0, c->stream);
+    if (ce != cudaSuccess) {
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+        return cuda_fail(c, ce, "cs_time_render_frame");
+    }
     for (int i = 0; i < iters; i++) { r = dispatch(c, P, 0, 0, c->W, c->H, c->d_image); if (r) break; }
     cudaEventRecord(e1, c->stream);
     cudaError_t e = cudaEventSynchronize(e1);

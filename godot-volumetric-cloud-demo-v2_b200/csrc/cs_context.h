@@ -62,8 +62,10 @@ struct cs_context {
 
 
 namespace cs {
-// prologue + march of one pixel rectangle into `out`, sampling `sky_lut` (nullptr = the context's own LUT).
-int ctx_dispatch(cs_context* c, const cs_cloud_params* P, int x0, int y0, int x1, int y1, uint16_t* out, const uint16_t* sky_lut);
+// prologue + march of one pixel rectangle into `out`, sampling `sky_lut` (nullptr = the context's own LUT).  `out` is an image of
+// img_w x img_h pixels owned by the caller (params.texture_size is validated against THAT size; the context's own image and size,
+// which other users of the context may rely on, are not touched).
+int ctx_dispatch(cs_context* c, const cs_cloud_params* P, int x0, int y0, int x1, int y1, uint16_t* out, const uint16_t* sky_lut, int img_w, int img_h);
 // sky-LUT kernel into `dst` (device half4[200*100]); requires the transmittance LUT.
 int ctx_build_sky_lut_into(cs_context* c, const float sun[3], uint16_t* dst);
 int ctx_fail(cs_context* c, int code, const std::string& msg);

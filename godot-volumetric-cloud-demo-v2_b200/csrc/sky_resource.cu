@@ -62,10 +62,6 @@ int update_performance(cs_sky* k) {
         CU(cudaMalloc(&k->tex[i], bytes));
         CU(cudaMemsetAsync(k->tex[i], 0, bytes, k->c->stream));  // the reference clears to debug colours (cloud_sky.gd:402)
     }
-    if (k->c->W != ts || k->c->H != ts) {  // keep the context's image size in step (params.texture_size is validated against it)
-        int r = cs_resize(k->c, ts, ts);
-        if (r) return r;
-    }
     k->can_run = true;
     return CS_OK;
 }
@@ -103,7 +99,8 @@ int render_process(cs_sky* k) {
     cs_fill_cloud_params(&p, &k->s, &k->fd, k->texture_size, k->texture_size, k->update_position[0], k->update_position[1]);
     const int x0 = k->update_position[0], y0 = k->update_position[1];
     const uint16_t* lut = k->lut[(k->sky_current + 2) % 3];  // sky_uniform_set[(sky_lut.current_texture + 2) % 3] (cloud_sky.gd:242)
-    return ctx_dispatch(k->c, &p, x0, y0, x0 + 8 * k->groups, y0 + 8 * k->groups, k->tex[k->to_update], lut);
+    // the sky's own texture size travels with the dispatch: the shared context is never resized under its other users
+    return ctx_dispatch(k->c, &p, x0, y0, x0 + 8 * k->groups, y0 + 8 * k->groups, k->tex[k->to_update], lut, k->texture_size, k->texture_size);
 }
 
 int update_sky(cs_sky* k, float now);

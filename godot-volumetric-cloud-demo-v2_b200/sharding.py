@@ -54,13 +54,15 @@ def sun_shard(n: int, world: int, rank: int) -> Tuple[int, int]:
 
 
 def _all_gather_inplace(full_flat, chunk, group=None):
+    """In-place all-gather of equal chunks.  The collective is chosen from the backend up front (never by catching an
+    error: a rank that retried with a different collective than its peers would hang the job)."""
     import torch.distributed as dist
-    try:
-        dist.all_gather_into_tensor(full_flat, chunk, group=group)
-    except (RuntimeError, NotImplementedError):  # backends without the flat variant
+    if dist.get_backend(group) == "gloo":  # CPU tests: gloo has no flat in-place variant
         world = dist.get_world_size(group)
         parts = list(full_flat.chunk(world))
         dist.all_gather(parts, chunk.clone(), group=group)
+    else:
+        dist.all_gather_into_tensor(full_flat, chunk, group=group)
 
 
 class ShardedRenderer:
@@ -75,18 +77,20 @@ class ShardedRenderer:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         if ctx.width != width or ctx.height != height:
             ctx.resize(width, height)
+        if device != "cpu":
+            # kernels, the output allocation and the NCCL all-gather must be ordered on ONE stream: the context's own stream is
+            # cudaStreamNonBlocking, so it would race torch's allocator/fill work and NCCL otherwise
+            self.use_torch_stream()
 
     def render_frame_rows(self, params, bands_per_rank: int = 1):
         """One frame split into row bands; returns the gathered [H, W, 4] fp16 tensor (identical on all ranks).
         bands_per_rank > 1 interleaves the bands over the ranks (interleaved_bands) to even out the lit fraction; the result is
         the same texture, gathered with one all-gather per band group."""
         torch = self.torch
-        full = torch.zeros((self.H, self.W, 4), dtype=torch.float16, device=self.device)
+        full = torch.empty((self.H, self.W, 4), dtype=torch.float16, device=self.device)  # every row is written by a render or the gather
         mine = interleaved_bands(self.H, self.world, bands_per_rank)[self.rank]
         for r0, r1 in mine:
             self.ctx.render_rows_to(params, r0, r1, full.data_ptr())
-        if self.device != "cpu":
-            self.ctx.sync() if self._own_stream() else None
         if self.world > 1:
             flat = full.view(-1)
             per = (mine[0][1] - mine[0][0]) * self.W * 4          # elements of one band
@@ -101,19 +105,13 @@ class ShardedRenderer:
         suns = np.asarray(suns, np.float32).reshape(-1, 3)
         n = suns.shape[0]
         k0, k1 = sun_shard(n, self.world, self.rank)
-        full = torch.zeros((n, self.H, self.W, 4), dtype=torch.float16, device=self.device)
+        full = torch.empty((n, self.H, self.W, 4), dtype=torch.float16, device=self.device)
         self.ctx.render_sun_batch_to(params, suns[k0:k1], full[k0].data_ptr())
-        if self.device != "cpu":
-            self.ctx.sync() if self._own_stream() else None
         if self.world > 1:
             flat = full.view(-1)
             per = (k1 - k0) * self.H * self.W * 4
             _all_gather_inplace(flat, flat[self.rank * per:(self.rank + 1) * per], self.group)
         return full
-
-    def _own_stream(self) -> bool:
-        # When the context renders on its own stream (not torch's), synchronise before handing the buffer to NCCL.
-        return not getattr(self.ctx, "_shares_torch_stream", False)
 
     def use_torch_stream(self):
         """Make the context launch on torch's current stream so kernels and the NCCL all-gather are stream-ordered."""

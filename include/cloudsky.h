@@ -291,7 +291,10 @@ typedef struct cs_sky_frame {
     cs_frame_state frame_data;     /* FrameData snapshot used by the texture being updated                        */
 } cs_sky_frame;
 /* load("clouds_sky.tres") + delayed_init (cloud_sky.gd:99-107): allocate the textures for settings->texture_size.
- * The context must already hold the input textures and the transmittance LUT. */
+ * The context must already hold the input textures and the transmittance LUT.  A sky owns its three textures and
+ * three sky LUTs and renders into them with its own texture size: the context's image and cs_resize() state are
+ * never changed by a sky, so several skies of different sizes may share one context.  Ownership: a cs_sky keeps a
+ * pointer to its context — destroy every sky BEFORE cs_destroy(ctx) (cleanup() order of cloud_sky.gd:197-212). */
 int cs_sky_create(cs_context* ctx, const cs_sky_settings* settings, cs_sky** out_sky);
 void cs_sky_destroy(cs_sky* sky);
 /* Property setters (cloud_sky.gd:4-50).  A change of texture_size or frames_to_update runs cleanup() +

@@ -115,6 +115,7 @@ def test_gpu_sky_tiles_equal_single_dispatch(cs, product_lib, small_textures, he
     tiled = sky.read_texture(finished)
     ctx.build_sky_lut(tuple(f.frame_data.light_direction))
     p = product_lib.fill_cloud_params(s, f.frame_data, 128, 128, 0, 0)
+    ctx.resize(128, 128)  # the sky renders into its own textures and leaves the context's image alone
     ctx.render_frame(p)
     assert (ctx.read_image().view(np.uint16) == tiled.view(np.uint16)).all()
     sky.close(); ctx.close()
