@@ -189,11 +189,13 @@ _PROTOTYPES = {
     "cs_write_sky_lut": (C.c_int, [_P, _P, C.c_size_t]),
     "cs_resize": (C.c_int, [_P, C.c_int, C.c_int]),
     "cs_set_march_config": (C.c_int, [_P, C.c_int, C.c_int, C.c_int]),
+    "cs_set_step_budget": (C.c_int, [_P, C.c_float, C.c_int]),
     "cs_set_counters_enabled": (C.c_int, [_P, C.c_int]),
     "cs_get_counters": (C.c_int, [_P, C.POINTER(Counters)]),
     "cs_dispatch_clouds": (C.c_int, [_P, C.POINTER(CloudParams), C.c_int, C.c_int]),
     "cs_render_frame": (C.c_int, [_P, C.POINTER(CloudParams)]),
     "cs_render_rows_to": (C.c_int, [_P, C.POINTER(CloudParams), C.c_int, C.c_int, _P]),
+    "cs_render_row_bands_to": (C.c_int, [_P, C.POINTER(CloudParams), C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "cs_image_device_ptr": (_P, [_P]),
     "cs_read_image": (C.c_int, [_P, _P, C.c_size_t]),
     "cs_render_frame_host": (C.c_int, [_P, C.POINTER(CloudParams), _P, C.c_size_t]),
@@ -201,6 +203,13 @@ _PROTOTYPES = {
     "cs_wait_host": (C.c_int, [_P]),
     "cs_render_sun_batch_to": (C.c_int, [_P, C.POINTER(CloudParams), C.POINTER(C.c_float), C.c_int, _P]),
     "cs_time_render_frame": (C.c_int, [_P, C.POINTER(CloudParams), C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    "cs_peer_alloc": (C.c_int, [_P, C.c_size_t, C.POINTER(_P), C.c_char_p]),
+    "cs_peer_open": (C.c_int, [_P, C.c_char_p, C.POINTER(_P)]),
+    "cs_peer_close": (C.c_int, [_P, _P]),
+    "cs_peer_free": (C.c_int, [_P, _P]),
+    "cs_set_output_mirrors": (C.c_int, [_P, _P, C.c_size_t, C.c_int, C.POINTER(_P)]),
+    "cs_peer_barrier": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P), C.c_uint32]),
+    "cs_peer_check": (C.c_int, [_P]),
     "cs_sky_create": (C.c_int, [_P, C.POINTER(SkySettings), C.POINTER(_P)]),
     "cs_sky_destroy": (None, [_P]),
     "cs_sky_set_settings": (C.c_int, [_P, C.POINTER(SkySettings)]),
@@ -419,6 +428,10 @@ class Context:
     def set_march_config(self, primary_steps: int = REF_PRIMARY_STEPS, cone_samples: int = REF_CONE_SAMPLES, mode: int = MODE_FAST) -> None:
         self._ck(self.lib.dll.cs_set_march_config(self._h, primary_steps, cone_samples, mode))
 
+    def set_step_budget(self, min_step_length_m: float = 0.0, min_steps: int = 1) -> None:
+        """Adaptive per-direction primary step count (0 = the reference's fixed count); see include/cloudsky.h."""
+        self._ck(self.lib.dll.cs_set_step_budget(self._h, float(min_step_length_m), int(min_steps)))
+
     def set_counters_enabled(self, on: bool) -> None:
         self._ck(self.lib.dll.cs_set_counters_enabled(self._h, int(on)))
 
@@ -435,6 +448,9 @@ class Context:
 
     def render_rows_to(self, params: CloudParams, row_begin: int, row_end: int, device_ptr: int) -> None:
         self._ck(self.lib.dll.cs_render_rows_to(self._h, C.byref(params), row_begin, row_end, _P(device_ptr)))
+
+    def render_row_bands_to(self, params: CloudParams, first_row: int, band_rows: int, band_pitch_rows: int, n_bands: int, device_ptr: int) -> None:
+        self._ck(self.lib.dll.cs_render_row_bands_to(self._h, C.byref(params), first_row, band_rows, band_pitch_rows, n_bands, _P(device_ptr)))
 
     def image_device_ptr(self) -> int:
         return int(self.lib.dll.cs_image_device_ptr(self._h) or 0)
@@ -465,6 +481,36 @@ class Context:
     def render_sun_batch_to(self, params: CloudParams, sun_dirs: np.ndarray, device_ptr: int) -> None:
         s = np.ascontiguousarray(sun_dirs, dtype=np.float32).reshape(-1, 3)
         self._ck(self.lib.dll.cs_render_sun_batch_to(self._h, C.byref(params), s.ctypes.data_as(C.POINTER(C.c_float)), s.shape[0], _P(device_ptr)))
+
+    # ---- multi-GPU: peer-mapped output replicas (fused all-gather) ----
+    def peer_alloc(self, nbytes: int):
+        """-> (device pointer, 64-byte IPC handle) of a zero-filled exportable buffer."""
+        ptr = _P()
+        handle = C.create_string_buffer(64)
+        self._ck(self.lib.dll.cs_peer_alloc(self._h, nbytes, C.byref(ptr), handle))
+        return ptr.value, handle.raw
+
+    def peer_open(self, handle: bytes) -> int:
+        ptr = _P()
+        self._ck(self.lib.dll.cs_peer_open(self._h, handle, C.byref(ptr)))
+        return ptr.value
+
+    def peer_close(self, ptr: int) -> None:
+        self._ck(self.lib.dll.cs_peer_close(self._h, _P(ptr)))
+
+    def peer_free(self, ptr: int) -> None:
+        self._ck(self.lib.dll.cs_peer_free(self._h, _P(ptr)))
+
+    def set_output_mirrors(self, base: int, nbytes: int, mirror_bases) -> None:
+        arr = (_P * max(1, len(mirror_bases)))(*mirror_bases)
+        self._ck(self.lib.dll.cs_set_output_mirrors(self._h, _P(base), nbytes, len(mirror_bases), arr))
+
+    def peer_barrier(self, rank: int, world: int, flag_arrays, epoch: int) -> None:
+        arr = (_P * world)(*flag_arrays)
+        self._ck(self.lib.dll.cs_peer_barrier(self._h, rank, world, arr, epoch & 0xFFFFFFFF))
+
+    def peer_check(self) -> None:
+        self._ck(self.lib.dll.cs_peer_check(self._h))
 
     def set_kernel_timing(self, on: bool) -> None:
         self._ck(self.lib.dll.cs_set_kernel_timing(self._h, int(on)))

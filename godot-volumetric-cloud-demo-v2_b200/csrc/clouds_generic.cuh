@@ -190,7 +190,9 @@ __device__ __forceinline__ V4 sky_pixel_ref(const cs::CloudLaunch& L, const cs::
     V3 start = camPos + dir * intersectSphere<STRICT>(camPos, dir, sky_b_radius);
     V3 end = camPos + dir * intersectSphere<STRICT>(camPos, dir, sky_t_radius);
     float shelldist = length3<STRICT>(end - start);
-    float steps = (float)L.primary_steps;
+    int n_steps = L.primary_steps;
+    if (L.budget_len > 0.0f) n_steps = min(L.primary_steps, max(L.budget_min, (int)ceilf(fdiv<STRICT>(shelldist, L.budget_len))));  // cs_set_step_budget
+    float steps = (float)n_steps;
     V3 ds = dir * shelldist;
     V3 raystep = {fdiv<STRICT>(ds.x, steps), fdiv<STRICT>(ds.y, steps), fdiv<STRICT>(ds.z, steps)};
 
@@ -217,7 +219,7 @@ __device__ __forceinline__ V4 sky_pixel_ref(const cs::CloudLaunch& L, const cs::
     const float weather_scale = 0.00006f;
     const float wpx = P.weather_pos[0], wpy = P.weather_pos[1];
 
-    for (int i = 0; i < L.primary_steps; i++) {
+    for (int i = 0; i < n_steps; i++) {
         if constexpr (COUNT) tl.steps++;
         p = p + d * ss;
         V3 weather_sample = sample_weather_rgba8(L.weather, L.weather_w, L.weather_h, p.x * weather_scale + 0.5f + wpx, p.z * weather_scale + 0.5f + wpy);

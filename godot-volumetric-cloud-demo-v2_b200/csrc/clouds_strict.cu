@@ -19,7 +19,9 @@ __global__ void clouds_prologue_kernel(const __grid_constant__ cs::CloudLaunch L
 
 template <bool COUNT>
 __global__ void __launch_bounds__(64) clouds_strict_kernel(const __grid_constant__ cs::CloudLaunch L) {
-    int px = L.x0 + blockIdx.x * 8 + threadIdx.x, py = L.y0 + blockIdx.y * 8 + threadIdx.y;  // 8x8 groups (clouds.glsl:5)
+    const int by = blockIdx.y, band = L.band_ctas ? by / L.band_ctas : 0;
+    const int row0 = L.band_ctas ? band * L.band_pitch_rows + (by - band * L.band_ctas) * 8 : by * 8;  // interleaved bands (cs_render_row_bands_to)
+    int px = L.x0 + blockIdx.x * 8 + threadIdx.x, py = L.y0 + row0 + threadIdx.y;  // 8x8 groups (clouds.glsl:5)
     if (px >= L.x1 || py >= L.y1) return;  // the reference does not bounds-check; we do
     const cs::FrameConsts fc = *reinterpret_cast<const cs::FrameConsts*>(L.frame_consts);
     V3 dir = pixel_direction<true>(px, py, L.P.texture_size[0], L.P.texture_size[1]);
@@ -28,7 +30,9 @@ __global__ void __launch_bounds__(64) clouds_strict_kernel(const __grid_constant
     bool marched = dir.y > 0.0f;  // clouds.glsl:221
     if (marched) col = sky_pixel_ref<true, COUNT>(L, fc, dir, tl);
     ushort4 o = {f2h(col.x), f2h(col.y), f2h(col.z), f2h(col.w)};
-    reinterpret_cast<ushort4*>(L.out)[(size_t)py * L.out_pitch_px + px] = o;
+    const size_t at = (size_t)py * L.out_pitch_px + px;
+    reinterpret_cast<ushort4*>(L.out)[at] = o;
+    for (int m = 0; m < L.n_mirrors; m++) reinterpret_cast<ushort4*>(L.mirror[m])[at] = o;
     if constexpr (COUNT) {
         atomicAdd(L.counters + 0, marched ? 1ull : 0ull);
         atomicAdd(L.counters + 1, (unsigned long long)tl.steps);
@@ -50,7 +54,7 @@ void launch_clouds_prologue(const CloudLaunch& L, bool strict, void* stream) {
 }
 
 void launch_clouds_strict(const CloudLaunch& L, void* stream) {
-    dim3 block(8, 8), grid((L.x1 - L.x0 + 7) / 8, (L.y1 - L.y0 + 7) / 8);
+    dim3 block(8, 8), grid((L.x1 - L.x0 + 7) / 8, L.grid_y > 0 ? L.grid_y : (L.y1 - L.y0 + 7) / 8);
     if (grid.x == 0 || grid.y == 0) return;
     if (L.counters) clouds_strict_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(L);
     else clouds_strict_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(L);

@@ -331,6 +331,7 @@ int make_launch(cs_context* c, const cs_cloud_params* P, int x0, int y0, int x1,
     L.x1 = x1 > IW ? IW : x1; L.y1 = y1 > IH ? IH : y1;
     L.out_pitch_px = IW;
     L.primary_steps = c->primary_steps; L.cone_samples = c->cone_samples;
+    L.budget_len = c->budget_len; L.budget_min = c->budget_min;
     // below 2^-12 the remaining radiance is < 1 fp16 ulp and alpha = 1 - T already rounds to 1.0 in fp16
     L.early_out_T = (c->mode & CS_MODE_EARLY_OUT) ? 0.000244140625f : 0.0f;
     L.large_n = c->large_n; L.large_levels = c->large_levels;
@@ -363,6 +364,14 @@ int make_launch(cs_context* c, const cs_cloud_params* P, int x0, int y0, int x1,
     L.out = out;
     L.counters = c->counters_on ? c->d_counters : nullptr;
     L.n_suns = 1; L.sun_stride_px = 0;
+    L.n_mirrors = 0;
+    if (c->n_mirrors > 0) {
+        const uint8_t* o = reinterpret_cast<const uint8_t*>(out);
+        if (o >= c->mirror_base && o < c->mirror_base + c->mirror_bytes) {  // `out` lies in the registered range: replicate at the same offset
+            L.n_mirrors = c->n_mirrors;
+            for (int m = 0; m < c->n_mirrors; m++) L.mirror[m] = reinterpret_cast<uint16_t*>(c->mirror_peer[m] + (o - c->mirror_base));
+        }
+    }
     return CS_OK;
 }
 
@@ -378,13 +387,14 @@ void timing_mark(cs_context* c, std::vector<cudaEvent_t>& evs, size_t pair, int 
 
 // prologue + march for one rectangle, asynchronous on c->stream
 int dispatch(cs_context* c, const cs_cloud_params* P, int x0, int y0, int x1, int y1, uint16_t* out, const uint16_t* sky_lut = nullptr,
-             int img_w = 0, int img_h = 0) {
+             int img_w = 0, int img_h = 0, int band_ctas = 0, int band_pitch_rows = 0, int n_bands = 0) {
     if (!c || !P) return CS_ERR_INVALID;
     int r = bind(c);
     if (r) return r;
     CloudLaunch L;
     r = make_launch(c, P, x0, y0, x1, y1, out, sky_lut, L, img_w, img_h);
     if (r) return r;
+    L.band_ctas = band_ctas; L.band_pitch_rows = band_pitch_rows; L.grid_y = band_ctas * n_bands;
     if (L.x1 <= L.x0 || L.y1 <= L.y0) return CS_OK;
     if (L.counters) CU(cudaMemsetAsync(c->d_counters, 0, 6 * sizeof(unsigned long long), c->stream));
     launch_clouds_prologue(L, c->mode == CS_MODE_STRICT, c->stream);
@@ -460,6 +470,7 @@ void cs_destroy(cs_context* c) {
     if (c->d_sky_batch) cudaFree(c->d_sky_batch);
     if (c->d_image) cudaFree(c->d_image);
     if (c->d_image2) cudaFree(c->d_image2);
+    if (c->d_peer_err) cudaFree(c->d_peer_err);
     for (int i = 0; i < 2; i++) {
         if (c->ev_rendered[i]) cudaEventDestroy(c->ev_rendered[i]);
         if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
@@ -671,6 +682,12 @@ int cs_set_march_config(cs_context* c, int p, int cone, int mode) {
     c->primary_steps = p; c->cone_samples = cone; c->mode = mode;
     return CS_OK;
 }
+int cs_set_step_budget(cs_context* c, float len, int min_steps) {
+    if (!c) return CS_ERR_INVALID;
+    if (!(len >= 0.0f) || min_steps < 1) return fail(c, CS_ERR_INVALID, "cs_set_step_budget: min_step_length_m >= 0, min_steps >= 1");
+    c->budget_len = len; c->budget_min = min_steps;
+    return CS_OK;
+}
 int cs_set_counters_enabled(cs_context* c, int on) {
     if (!c) return CS_ERR_INVALID;
     c->counters_on = on != 0;
@@ -723,6 +740,12 @@ int cs_render_frame(cs_context* c, const cs_cloud_params* P) {
 int cs_render_rows_to(cs_context* c, const cs_cloud_params* P, int r0, int r1, void* out) {
     if (!c || !P || !out) return CS_ERR_INVALID;
     return dispatch(c, P, 0, r0, c->W, r1, (uint16_t*)out);
+}
+int cs_render_row_bands_to(cs_context* c, const cs_cloud_params* P, int first_row, int band_rows, int band_pitch_rows, int n_bands, void* out) {
+    if (!c || !P || !out) return CS_ERR_INVALID;
+    if (first_row < 0 || band_rows < 8 || band_rows % 8 != 0 || band_pitch_rows < band_rows || n_bands < 1 || n_bands > 65535 / (band_rows / 8))
+        return fail(c, CS_ERR_INVALID, "cs_render_row_bands_to: band_rows must be a positive multiple of 8, band_pitch_rows >= band_rows, n_bands >= 1");
+    return dispatch(c, P, 0, first_row, c->W, c->H, (uint16_t*)out, nullptr, 0, 0, band_rows / 8, band_pitch_rows, n_bands);
 }
 void* cs_image_device_ptr(cs_context* c) { return c ? c->d_image : nullptr; }
 int cs_read_image(cs_context* c, uint16_t* out, size_t bytes) {

@@ -49,8 +49,17 @@ struct cs_context {
     bool slot_busy[2] = {false, false};
     unsigned async_frame = 0;
 
+    // fused all-gather: peer replicas of a registered output range (cs_set_output_mirrors)
+    uint8_t* mirror_base = nullptr;
+    size_t mirror_bytes = 0;
+    int n_mirrors = 0;
+    uint8_t* mirror_peer[cs::kMaxMirrors] = {};
+    unsigned* d_peer_err = nullptr;  // set by the peer barrier kernel when a peer never arrives
+
     // march config
     int primary_steps = CS_REF_PRIMARY_STEPS, cone_samples = CS_REF_CONE_SAMPLES, mode = CS_MODE_FAST;
+    float budget_len = 0.0f;  // cs_set_step_budget
+    int budget_min = 1;
     bool counters_on = false;
     unsigned long long* d_counters = nullptr;
 

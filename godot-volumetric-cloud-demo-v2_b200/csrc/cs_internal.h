@@ -13,6 +13,7 @@ namespace cs {
 constexpr int kMaxLargeLevels = 8;  // 128 -> 1
 constexpr int kMaxSmallLevels = 6;  // 32 -> 1
 constexpr int kMaxSunBatch = 4;     // suns marched together by the sun-batch kernel (cs_render_sun_batch_to)
+constexpr int kMaxMirrors = 7;      // peer replicas of the output a march kernel also stores to (cs_set_output_mirrors): 8 GPUs - 1
 
 // ---- host-side assets (assets.cpp) ----------------------------------------------------------
 struct HostImage {
@@ -35,7 +36,12 @@ struct CloudLaunch {
     int width, height;        // image size (== P.texture_size)
     int x0, y0, x1, y1;       // pixel rectangle to render (already clipped)
     int out_pitch_px;         // row pitch of out, in pixels
+    // Interleaved row bands in ONE launch (cs_render_row_bands_to; multi-GPU strong scaling of a single frame): CTA row `by` renders image
+    // rows y0 + (by / band_ctas) * band_pitch_rows + (by % band_ctas) * 8 ...  band_ctas == 0: contiguous rows from y0 (the default).
+    int band_ctas, band_pitch_rows, grid_y;
     float early_out_T;        // 0: run every primary step like the reference; > 0: CS_MODE_EARLY_OUT transmittance threshold
+    float budget_len;         // > 0: cs_set_step_budget — steps(dir) = clamp(ceil(shell length / budget_len), budget_min, primary_steps)
+    int budget_min;
     int primary_steps;        // 128 in the reference
     int cone_samples;         // 6 in the reference
     int large_n, large_levels;
@@ -64,6 +70,10 @@ struct CloudLaunch {
     unsigned long long* counters;               // 6 x u64 or nullptr
     int n_suns;                                 // sun-batch kernel: frame_consts holds this many FrameConsts, out this many images
     size_t sun_stride_px;                       // pixels between consecutive images of a sun batch
+    // Fused all-gather (cs_set_output_mirrors): every finished pixel is also stored, at the same offset, into these
+    // peer-mapped replicas of the output buffer (other GPUs' memory, reached over NVLink by plain st.global).
+    int n_mirrors;
+    uint16_t* mirror[kMaxMirrors];
 };
 
 // Pixel-independent values of march()'s prologue (clouds.glsl:149-167), computed once per

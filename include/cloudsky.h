@@ -228,6 +228,16 @@ int cs_resize(cs_context* ctx, int width, int height);
  * RANDOM_VECTORS[j % 6] * j and mip j, LODs clamp to the last mip. */
 int cs_set_march_config(cs_context* ctx, int primary_steps, int cone_samples, int mode);
 /* Enable/disable the device work counters (slower instrumented kernel when enabled). */
+/* Adaptive primary step count per direction (extension; the reference's own unimplemented hint "Take fewer steps towards
+ * horizon", clouds.glsl:227, and BASELINE configs[4]'s "hierarchical/adaptive step"): never step finer than
+ * min_step_length_m along a ray —
+ *     steps(dir) = clamp(ceil(shell_length(dir) / min_step_length_m), min_steps, primary_steps)
+ * so directions whose slab crossing is short (towards the zenith: 2.5 km vs 84.8 km at the horizon) take fewer than
+ * primary_steps steps.  min_step_length_m = 0 (default) restores the reference's fixed count.  NOT reference behaviour: it
+ * changes the sample positions.  Measured against the fixed-count render: inside the parity tolerance
+ * for optically thick skies (coverage 1.0: 100 % of pixels at 19.53 m, the reference's own zenith step), outside it for thin
+ * cloud (coverage 0.2).  cs_counters reports the executed steps. */
+int cs_set_step_budget(cs_context* ctx, float min_step_length_m, int min_steps);
 int cs_set_counters_enabled(cs_context* ctx, int enabled);
 int cs_get_counters(cs_context* ctx, cs_counters* out);
 
@@ -244,6 +254,14 @@ int cs_render_frame(cs_context* ctx, const cs_cloud_params* params);
 int cs_render_rows_to(cs_context* ctx, const cs_cloud_params* params, int row_begin, int row_end,
                       void* device_out_half4);
 /* Device pointer of the context-owned output image (Texture2DRD handle, cloud_sky.gd:235). */
+/* Interleaved row bands of one frame in ONE launch: bands b = 0 .. n_bands-1 cover rows
+ * [first_row + b * band_pitch_rows, + band_rows) (clipped to the image); band_rows is a multiple of 8 (the 8x8 workgroup of
+ * clouds.glsl:5 / one CTA row).  This is the multi-GPU strong-scaling shard of a single frame: rank r of N
+ * calls it with first_row = r * band_rows, band_pitch_rows = N * band_rows, so the lit fraction — which varies with the
+ * row — is spread evenly over the ranks; tiles are independent like the reference's update_position tiles
+ * (cloud_sky.gd:156-161), so the assembled image is bit-identical to one full dispatch. */
+int cs_render_row_bands_to(cs_context* ctx, const cs_cloud_params* params, int first_row, int band_rows, int band_pitch_rows,
+                           int n_bands, void* device_out_half4);
 void* cs_image_device_ptr(cs_context* ctx);
 /* Copy the context-owned image to host: tightly packed half4[W*H], row 0 = uv.y 0. */
 int cs_read_image(cs_context* ctx, uint16_t* out_half4, size_t out_bytes);
@@ -269,6 +287,34 @@ int cs_render_sun_batch_to(cs_context* ctx, const cs_cloud_params* params, const
  * context's stream (after `warmup` untimed ones).  Returns average milliseconds per dispatch. */
 int cs_time_render_frame(cs_context* ctx, const cs_cloud_params* params, int warmup, int iters,
                          float* out_ms_avg);
+
+/* ---- multi-GPU: fused all-gather through peer-mapped output replicas -------------------------
+ * The reference renders its texture as independent tiles addressed by update_position (cloud_sky.gd:156-161) and every
+ * pixel depends on nothing but the push constants and the textures (clouds.glsl:258-266), so ranks (one process per GPU)
+ * render disjoint tiles / sun angles with no exchange while rendering.  The gather of the finished texture is fused into
+ * the march kernel: each rank holds a full copy of the gathered buffer, maps its peers' copies (CUDA IPC over
+ * NVLink/NVSwitch peer access) and the kernel stores every finished pixel into all copies.  cs_peer_barrier is what is
+ * left of the collective: "my stores have landed everywhere, and so have everyone else's".
+ * Host protocol per rank: cs_peer_alloc (buffer + 64-byte handle) -> exchange handles out of band (torch.distributed,
+ * MPI, a file ...) -> cs_peer_open each peer's handle -> cs_set_output_mirrors -> render with the ordinary calls
+ * (cs_render_rows_to / cs_render_sun_batch_to into the own copy) -> cs_peer_barrier.  CUDA-only. */
+#define CS_IPC_HANDLE_BYTES 64
+/* cudaMalloc'ed, zero-filled, exportable device buffer + its IPC handle. */
+int cs_peer_alloc(cs_context* ctx, size_t bytes, void** out_device_ptr, uint8_t out_handle[CS_IPC_HANDLE_BYTES]);
+/* Map a peer's buffer (the handle came from cs_peer_alloc in another process on the same node). */
+int cs_peer_open(cs_context* ctx, const uint8_t handle[CS_IPC_HANDLE_BYTES], void** out_device_ptr);
+int cs_peer_close(cs_context* ctx, void* opened_device_ptr);
+int cs_peer_free(cs_context* ctx, void* allocated_device_ptr);
+/* From now on every march dispatch whose output pointer lies inside [base, base + bytes) also stores each finished pixel
+ * at the same offset into mirror_bases[0 .. n_mirrors) (peer-mapped copies; n_mirrors <= 7).  n_mirrors = 0 turns it off. */
+int cs_set_output_mirrors(cs_context* ctx, void* base, size_t bytes, int n_mirrors, void* const* mirror_bases);
+/* Stream-ordered completion barrier of the fused gather: flag_arrays[k] is rank k's flag array (>= world uint32, from
+ * cs_peer_alloc; the own one at [rank], peers' opened with cs_peer_open).  Queues one tiny kernel that publishes `epoch`
+ * (any value increasing by < 2^31 per call) to every rank and waits until every rank published it.  After it, on this
+ * context's stream, the own copy holds every rank's pixels.  A rank that never arrives trips a ~20 s watchdog, reported by
+ * cs_peer_check (which synchronises the stream). */
+int cs_peer_barrier(cs_context* ctx, int rank, int world, void* const* flag_arrays, uint32_t epoch);
+int cs_peer_check(cs_context* ctx);
 
 /* ---- time-sliced update + temporal blend: the Sky resource of cloud_sky.gd ---------- */
 

@@ -453,6 +453,10 @@ struct CloudCtx {
     int hier_stride = 0;        // > 1: hierarchical-march STUDY (README.md:28 TODO, not reference behaviour; cso_set_hierarchical)
     float hier_margin = 0.0f;
     int hier_lod_bias = 0;
+    // per-direction step budget STUDY (clouds.glsl:227 "Take fewer steps towards horizon", never implemented there; cso_set_step_budget):
+    // steps(dir) = clamp(ceil(shell length / budget_len), budget_min, primary_steps); 0 = the reference's fixed count
+    float budget_len = 0.0f;
+    int budget_min = 1;
 };
 struct Tally { uint64_t px = 0, steps = 0, lit = 0, evals = 0; };
 
@@ -658,9 +662,11 @@ V4 sky(const CloudCtx& c, V3 dir, Tally& tl) {
         V3 start = camPos + dir * intersectSphere(camPos, dir, sky_b_radius);
         V3 end = camPos + dir * intersectSphere(camPos, dir, sky_t_radius);
         float shelldist = length3(end - start);
-        float steps = (float)c.primary_steps;  // 128.0 in the reference (:228)
+        int n_steps = c.primary_steps;
+        if (c.budget_len > 0.0f) n_steps = std::min(c.primary_steps, std::max(c.budget_min, (int)ceilf(shelldist / c.budget_len)));
+        float steps = (float)n_steps;  // 128.0 in the reference (:228)
         V3 raystep = (dir * shelldist) / steps;
-        col = march(c, start, end, raystep, c.primary_steps, tl);
+        col = march(c, start, end, raystep, n_steps, tl);
     }
     return col;
 }
@@ -714,6 +720,8 @@ struct cs_context {
     int primary_steps = CS_REF_PRIMARY_STEPS, cone_samples = CS_REF_CONE_SAMPLES;
     int hier_stride = 0, hier_lod_bias = 0;
     float hier_margin = 0.0f;
+    float budget_len = 0.0f;
+    int budget_min = 1;
     cs_counters counters{};
 };
 
@@ -817,6 +825,11 @@ int cs_set_march_config(cs_context* c, int p, int cone, int) {
     if (!c || p < 1 || p > 4096 || cone < 0 || cone > 64) return fail(c, CS_ERR_INVALID, "bad march config");
     c->primary_steps = p; c->cone_samples = cone; return CS_OK;
 }
+int cs_set_step_budget(cs_context* c, float step_len_m, int min_steps) {  // include/cloudsky.h: per-direction primary-step budget (0 = fixed count)
+    if (!c) return CS_ERR_INVALID;
+    if (!(step_len_m >= 0.0f) || min_steps < 1) return fail(c, CS_ERR_INVALID, "cs_set_step_budget: min_step_length_m >= 0, min_steps >= 1");
+    c->budget_len = step_len_m; c->budget_min = min_steps; return CS_OK;
+}
 int cs_set_counters_enabled(cs_context*, int) { return CS_OK; }
 int cs_get_counters(cs_context* c, cs_counters* out) { if (!c || !out) return CS_ERR_INVALID; *out = c->counters; return CS_OK; }
 
@@ -828,6 +841,7 @@ static int render_region(cs_context* c, const cs_cloud_params* P, int x0, int y0
     x0 = std::max(x0, 0); y0 = std::max(y0, 0); x1 = std::min(x1, c->W); y1 = std::min(y1, c->H);
     CloudCtx cc{&c->large, &c->small, &c->weather, c->skylut.data(), *P, c->primary_steps, c->cone_samples};
     cc.hier_stride = c->hier_stride; cc.hier_margin = c->hier_margin; cc.hier_lod_bias = c->hier_lod_bias;
+    cc.budget_len = c->budget_len; cc.budget_min = c->budget_min;
     std::vector<Tally> tl((size_t)std::max(c->threads, 1));
     parallel_rows(c->threads, std::max(y1 - y0, 0), [&](int r, int t) {
         int y = y0 + r;
@@ -855,6 +869,18 @@ int cs_render_frame(cs_context* c, const cs_cloud_params* P) {
 int cs_render_rows_to(cs_context* c, const cs_cloud_params* P, int r0, int r1, void* out) {
     if (!c || !P || !out) return CS_ERR_INVALID;
     return render_region(c, P, 0, r0, c->W, r1, (uint16_t*)out);  // "device" memory is host memory here
+}
+int cs_render_row_bands_to(cs_context* c, const cs_cloud_params* P, int first_row, int band_rows, int band_pitch_rows, int n_bands, void* out) {
+    if (!c || !P || !out) return CS_ERR_INVALID;
+    if (first_row < 0 || band_rows < 8 || band_rows % 8 != 0 || band_pitch_rows < band_rows || n_bands < 1)
+        return fail(c, CS_ERR_INVALID, "cs_render_row_bands_to: band_rows must be a positive multiple of 8, band_pitch_rows >= band_rows, n_bands >= 1");
+    for (int b = 0; b < n_bands; b++) {  // independent tiles (cloud_sky.gd:156-161): the oracle simply renders them one after the other
+        const int r0 = first_row + b * band_pitch_rows;
+        if (r0 >= c->H) break;
+        int r = render_region(c, P, 0, r0, c->W, std::min(r0 + band_rows, c->H), (uint16_t*)out);
+        if (r) return r;
+    }
+    return CS_OK;
 }
 void* cs_image_device_ptr(cs_context* c) { return c ? c->image.data() : nullptr; }
 int cs_read_image(cs_context* c, uint16_t* out, size_t bytes) {
@@ -884,6 +910,14 @@ int cs_time_render_frame(cs_context* c, const cs_cloud_params*, int, int, float*
 }
 
 int cs_set_kernel_timing(cs_context* c, int) { return fail(c, CS_ERR_UNSUPPORTED, "device timing is CUDA-only"); }
+// peer-mapped output replicas are a CUDA/NVLink mechanism; the oracle renders into host memory (gloo tests gather with torch)
+int cs_peer_alloc(cs_context* c, size_t, void**, uint8_t*) { return fail(c, CS_ERR_UNSUPPORTED, "peer buffers are CUDA-only"); }
+int cs_peer_open(cs_context* c, const uint8_t*, void**) { return fail(c, CS_ERR_UNSUPPORTED, "peer buffers are CUDA-only"); }
+int cs_peer_close(cs_context* c, void*) { return fail(c, CS_ERR_UNSUPPORTED, "peer buffers are CUDA-only"); }
+int cs_peer_free(cs_context* c, void*) { return fail(c, CS_ERR_UNSUPPORTED, "peer buffers are CUDA-only"); }
+int cs_set_output_mirrors(cs_context* c, void*, size_t, int, void* const*) { return fail(c, CS_ERR_UNSUPPORTED, "peer buffers are CUDA-only"); }
+int cs_peer_barrier(cs_context* c, int, int, void* const*, uint32_t) { return fail(c, CS_ERR_UNSUPPORTED, "peer buffers are CUDA-only"); }
+int cs_peer_check(cs_context* c) { return fail(c, CS_ERR_UNSUPPORTED, "peer buffers are CUDA-only"); }
 int cs_read_kernel_timings(cs_context* c, float*, int*, float*, int*) { return fail(c, CS_ERR_UNSUPPORTED, "device timing is CUDA-only"); }
 
 // ---- noise synthesis (cs_generate_noise; README.md:30 TODO) ----------------------------------------

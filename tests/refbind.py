@@ -119,8 +119,14 @@ class Reference:
             go(width, height)
         else:
             ux, uy = p[2], p[3]
-            for r_ in rows:
-                p[2], p[3] = 0.0, float(r_)
-                go(width, 1)
+            rows = sorted(int(r_) for r_ in rows)
+            i = 0
+            while i < len(rows):  # runs of consecutive rows become one W x n dispatch at update_position = (0, first row)
+                j = i
+                while j + 1 < len(rows) and rows[j + 1] == rows[j] + 1:
+                    j += 1
+                p[2], p[3] = 0.0, float(rows[i])
+                go(width, j - i + 1)
+                i = j + 1
             p[2], p[3] = ux, uy
         return img

@@ -53,7 +53,17 @@ def _worker(rank, world, port, out_dir):
     inter = r.render_frame_rows(p, bands_per_rank=4).numpy()  # interleaved bands, one all-gather per band group
     assert (inter.view(np.uint16) == frame.view(np.uint16)).all()
     sweep = r.render_sun_sweep(p, sharding.sun_sweep(4)).numpy()
-    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), frame=frame, sweep=sweep)
+    # bands of 8 rows: the rank's interleaved bands are ONE cs_render_row_bands_to call (the GPU path's single launch)
+    W2, H2 = 24, 64
+    ctx.resize(W2, H2)
+    ctx.build_sky_lut((0.0, 1.0, 0.0))  # the sweep left every rank with the LUT of its own last sun
+    r2 = sharding.ShardedRenderer(ctx, W2, H2, device="cpu")
+    p2 = make_params(lib, W2, H2, time=3.0, coverage=0.6)
+    tall = r2.render_frame_rows(p2, bands_per_rank=1).numpy()
+    for bpr in (2, 4, "max"):
+        again = r2.render_frame_rows(p2, bands_per_rank=bpr).numpy()
+        assert (again.view(np.uint16) == tall.view(np.uint16)).all(), bpr
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), frame=frame, sweep=sweep, tall=tall)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -85,3 +95,10 @@ def test_two_rank_gloo_matches_single_rank(cs, oracle_lib, helpers, tmp_path):
         for k in range(4):
             assert (d["sweep"][k].view(np.uint16) == singles[k].view(np.uint16)).all()
     assert single.astype(np.float32)[..., 3].max() > 0
+    # the 24x64 frame rendered with interleaved 8-row bands (one cs_render_row_bands_to call per rank) == one dispatch
+    ctx.resize(24, 64)
+    ctx.build_sky_lut((0.0, 1.0, 0.0))
+    p2 = helpers.make_params(oracle_lib, 24, 64, time=3.0, coverage=0.6)
+    ctx.render_frame(p2)
+    for rank in range(2):
+        assert (np.load(tmp_path / f"rank{rank}.npz")["tall"].view(np.uint16) == ctx.read_image().view(np.uint16)).all()

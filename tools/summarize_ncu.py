@@ -47,7 +47,9 @@ def main():
     if kernels and roofline_out:
         k = kernels[-1]
         hit = lambda name: float(k["metrics"][name]["value"]) if name in k["metrics"] else None
-        json.dump({"dram_bytes_per_launch": k["dram_bytes"], "kernel": k["kernel"], "l2_hit_pct": hit("lts__t_sector_hit_rate.pct"),
+        json.dump({"dram_bytes_per_launch": k["dram_bytes"], "kernel": k["kernel"], "warp_instructions_per_launch": hit("smsp__inst_executed.sum"),
+                   "kernel_ms_under_ncu": (hit("gpu__time_duration.sum") or 0.0) * {"us": 1e-3, "usecond": 1e-3, "ms": 1.0, "msecond": 1.0, "ns": 1e-6, "nsecond": 1e-6, "s": 1e3, "second": 1e3}.get(k["metrics"].get("gpu__time_duration.sum", {}).get("unit"), 1e-3),
+                   "l2_hit_pct": hit("lts__t_sector_hit_rate.pct"),
                    "l1_hit_pct": hit("l1tex__t_sector_hit_rate.pct"), "issue_active_pct": hit("smsp__issue_active.avg.pct_of_peak_sustained_active"), "source": f"{out} (ncu --set full --clock-control none: dram__bytes_read.sum + dram__bytes_write.sum)"},
                   open(roofline_out, "w"), indent=1)
     print(json.dumps({k["kernel"]: k["dram_bytes"] for k in kernels}))
