@@ -13,9 +13,9 @@ host, rebuild the sky LUT, run the march prologue and the march kernel for the w
 
 Metric: Mray-steps/s = marched pixels (dir.y > 0) x nominal primary steps / seconds / 1e6.
 
-N > 1 (launched under torchrun, one rank per GPU): weak scaling over sun-angle batches
-(BASELINE configs[3]): every rank renders one full frame for its own sun angle straight into its
-slice of the gathered [N, H, W, 4] fp16 buffer; the all-gather is FUSED into the march kernel (each
+N > 1 (launched under torchrun, one rank per GPU): weak scaling of the same workload — step k renders
+the N consecutive wind frames k*N .. k*N+N-1, one per rank, every rank straight into its slice of the
+gathered [N, H, W, 4] fp16 buffer; the all-gather is FUSED into the march kernel (each
 finished pixel is stored into every rank's copy over NVLink, godot-volumetric-cloud-demo-v2_b200/csrc/peer.cu)
 and completed by one flag barrier per step; value = N frames' ray-steps / max-over-ranks device time.
 `--gather nccl` uses one ncclAllGather per step on a side stream instead (the round-1 path).
@@ -47,21 +47,17 @@ N_SM = 148
 def bench_config(world):
     """The workload description — identical in both arms (the driver compares the two `config` objects)."""
     return {"workload": WORKLOAD, "width": W, "height": H, "primary_steps": PRIMARY, "light_steps": LIGHT, "cone_samples": CONE,
-            "animation": "step k renders wind frame k mod 16, t_k = 1 + k*64/60 s (cloud_sky.gd:165-187)",
-            "sun": "noon (0,1,0)" if world == 1 else f"rank r of {world}: (cos th, sin th, 0), th = pi (r + 0.5) / {world} (SURVEY 8(d) C4)",
+            "animation": "wind frame j has t_j = 1 + j*64/60 s (cloud_sky.gd:165-187), 16 frames cycled; step k renders frame k (N = 1) / frames k*N .. k*N+N-1, one per rank (N > 1)",
+            "sun": "noon (0,1,0)",
             "l2": f"GPU arm: flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB memset outside the per-step event pairs); CPU arm: not applicable",
-            "parallelism": "1 GPU" if world == 1 else f"{world} GPUs, weak scaling: one sun-angle frame per rank per step, gathered on every rank"}
+            "parallelism": "1 GPU" if world == 1 else f"{world} GPUs, weak scaling: {world} consecutive wind frames per step, one per rank, gathered on every rank"}
 
 
 def frame_time(k):
     return 1.0 + k * (64.0 / 60.0)  # SURVEY §8(d) C3
 
 
-def sun_for_rank(rank, world):
-    if world == 1:
-        return (0.0, 1.0, 0.0)
-    th = math.pi * (rank + 0.5) / world  # SURVEY §8(d) C4: dir_k = (cos th_k, sin th_k, 0)
-    return (math.cos(th), math.sin(th), 0.0)
+NOON = (0.0, 1.0, 0.0)
 
 
 def frame_params(lib, k, sun, width=W, height=H, coverage=None):
@@ -378,7 +374,7 @@ def run_ours(args):
     ctx.resize(W, H)
     base_mode = cs.MODE_FAST | (cs.MODE_TEX if args.sampler == "texture" else 0)
     ctx.set_march_config(PRIMARY, CONE, base_mode)
-    sun = sun_for_rank(rank, world)
+    sun = NOON
     frame_bytes = W * H * 8
 
     # ---- gathered output: [world, H, W, 4] fp16 on every rank, two slots -----------------------------------------------
@@ -425,7 +421,7 @@ def run_ours(args):
     counters_avg = {key: sum(c[key] for c in counters_all) / 16.0 for key in counters}
 
     def step(k):
-        p = params[k % 16]
+        p = params[(k * world + rank) % 16]  # N = 1: frame k; N ranks: frames k*N .. k*N+N-1, this rank's is k*N + rank
         b = k % len(gathered)
         buf = gathered[b]
         if gather == "nccl" and gather_used[b]:
@@ -509,24 +505,20 @@ def run_ours(args):
     ms_per_step = dev_ms / args.steps
 
     # ---- gather bit-identity (the driver's 1-GPU test box skips the multi-GPU tests): the last two steps' gathered buffers must
-    # hold, in the slice of rank (r+1) % N, exactly what this rank renders locally for that rank's sun -------------------------
+    # hold, in the slice of rank (r+1) % N, exactly what this rank renders locally for that rank's frame -----------------------
     gather_bit_identical = None
     if world > 1:
         torch.cuda.synchronize()
         dist.barrier()
         nb = (rank + 1) % world
-        nsun = sun_for_rank(nb, world)
         last = args.warmup + args.steps + (soak["steps"] if soak else 0) - 1
         okb = True
         check = torch.empty((H, W, 4), dtype=torch.float16, device="cuda")
-        ctx.build_sky_lut(nsun)
         for k in (last - 1, last):
-            q = frame_params(lib, k % 16, nsun)
-            ctx.render_rows_to(q, 0, H, check.data_ptr())
+            ctx.render_rows_to(params[(k * world + nb) % 16], 0, H, check.data_ptr())
             ctx.sync()
             okb = okb and bool(torch.equal(check.view(torch.int16), gathered[k % len(gathered)][nb].view(torch.int16)))
         gather_bit_identical = allmin_flag(okb)
-        ctx.build_sky_lut(sun)
         dist.barrier()
 
     # ---- end-to-end through the C-ABI with HOST buffers ------------------------------------------------------------------------
@@ -583,7 +575,7 @@ def run_ours(args):
 
     # ---- frame-0 kernel time (the launch the committed ncu capture profiles) -----------------------------------------------------
     ctx.build_sky_lut(sun)
-    frame0_ms = ctx.time_render_frame(params[0], 3, 10) if world == 1 else None
+    frame0_ms = ctx.time_render_frame(params[0], 3, 10)
 
     extra = {}
     # Extra, NOT the headline: the opt-in CS_MODE_EARLY_OUT flag (rays stop once T < 2^-12; results within 2 fp16 ulps,
@@ -622,8 +614,6 @@ def run_ours(args):
     peak, peak_src = measured_peak()
     march_ms = kt["march_ms"] / max(1, kt["march_launches"])
     capture = ncu_capture("roofline_tex.json" if args.sampler == "texture" else "roofline_latest.json")
-    if world > 1:  # the capture profiles the noon-sun frame of the 1-GPU run; ranks of an N-GPU run render other suns
-        capture = {k: v for k, v in capture.items() if k != "warp_instructions_per_launch"}
     roofline = build_roofline("clouds_fast_kernel", march_ms, frame0_ms if frame0_ms else march_ms, counters_avg, counters, clocks, capture, peak, peak_src)
     line = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",

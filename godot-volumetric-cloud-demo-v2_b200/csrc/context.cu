@@ -257,7 +257,10 @@ int upload_levels(cs_context* c, const std::vector<uint8_t>& large0, int ln, con
     const bool force_fp32_records = getenv("CLOUDSKY_FP32_RECORDS") != nullptr;  // development / test knob
     if (!is_pow2(ln) || !is_pow2(sn) || !is_pow2(ww) || !is_pow2(wh))
         return fail(c, CS_ERR_INVALID, "texture dimensions must be powers of two (REPEAT addressing uses masks)");
-    if (ln > 128 || sn > 32) return fail(c, CS_ERR_INVALID, "volume too large (large <= 128^3, small <= 32^3)");
+    // Sizes: the round-down-add floor of the kernel needs |coordinate * edge| < 2^22 at the slab's 6e6 m world coordinates
+    // (clouds.glsl:43-45 with the texture scales of :117,132,174): large <= 512, small <= 256, weather <= 8192.
+    if (ln > (1 << (kMaxLargeLevels - 1)) || sn > (1 << (kMaxSmallLevels - 1)) || ww > 8192 || wh > 8192)
+        return fail(c, CS_ERR_INVALID, "texture too large (large <= 512^3, small <= 256^3, weather <= 8192^2)");
     int r = bind(c);
     if (r) return r;
     CU(cudaStreamSynchronize(c->stream));

@@ -55,6 +55,7 @@ struct cs_context {
     int n_mirrors = 0;
     uint8_t* mirror_peer[cs::kMaxMirrors] = {};
     unsigned* d_peer_err = nullptr;  // set by the peer barrier kernel when a peer never arrives
+    long long peer_watchdog_cycles = 0;
 
     // march config
     int primary_steps = CS_REF_PRIMARY_STEPS, cone_samples = CS_REF_CONE_SAMPLES, mode = CS_MODE_FAST;

@@ -10,8 +10,8 @@
 
 namespace cs {
 
-constexpr int kMaxLargeLevels = 8;  // 128 -> 1
-constexpr int kMaxSmallLevels = 6;  // 32 -> 1
+constexpr int kMaxLargeLevels = 10;  // up to 512^3 -> 1 (the reference asset is 128^3: 8 levels)
+constexpr int kMaxSmallLevels = 9;   // up to 256^3 -> 1 (the reference asset is 32^3: 6 levels)
 constexpr int kMaxSunBatch = 4;     // suns marched together by the sun-batch kernel (cs_render_sun_batch_to)
 constexpr int kMaxMirrors = 7;      // peer replicas of the output a march kernel also stores to (cs_set_output_mirrors): 8 GPUs - 1
 

@@ -122,9 +122,12 @@ int cs_peer_barrier(cs_context* c, int rank, int world, void* const* flag_arrays
         if (!flag_arrays[k]) return ctx_fail(c, CS_ERR_INVALID, "cs_peer_barrier: null flag array");
         f.ptr[k] = (unsigned*)flag_arrays[k];
     }
-    int khz = 0;
-    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, c->device);
-    const long long watchdog = (long long)(khz > 0 ? khz : 2000000) * 1000ll * 20ll;  // ~20 s of SM clocks
+    if (c->peer_watchdog_cycles == 0) {  // queried once: device-attribute calls take a driver-wide lock (milliseconds with 8 busy processes)
+        int khz = 0;
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, c->device);
+        c->peer_watchdog_cycles = (long long)(khz > 0 ? khz : 2000000) * 1000ll * 20ll;  // ~20 s of SM clocks
+    }
+    const long long watchdog = c->peer_watchdog_cycles;
     peer_barrier_kernel<<<1, 32, 0, c->stream>>>(f, rank, world, epoch, c->d_peer_err, watchdog);
     CU(cudaGetLastError());
     return CS_OK;

@@ -108,6 +108,7 @@ class PeerBuffers:
             self.flag_ptrs.append(self.flags if k == self.rank else ctx.peer_open(fh))
         self.epoch = 0
         self.active = False
+        self._views = {}
 
     def activate(self):
         self.ctx.set_output_mirrors(self.base, self.nbytes, [b for k, b in enumerate(self.bases) if k != self.rank])
@@ -126,14 +127,20 @@ class PeerBuffers:
         self.ctx.peer_barrier(self.rank, self.world, self.flag_ptrs, self.epoch)
 
     def tensor(self, slot: int, shape, dtype="float16"):
+        """torch view of this rank's copy of `slot` (cached: the view is created once per slot and shape)."""
         import torch
-        typestr = {"float16": "<f2", "uint8": "|u1"}[dtype]
-        return torch.as_tensor(_DevicePtr(self.slot_ptr(slot), shape, typestr), device="cuda")
+        key = (slot % self.slots, tuple(shape), dtype)
+        t = self._views.get(key)
+        if t is None:
+            typestr = {"float16": "<f2", "uint8": "|u1"}[dtype]
+            t = self._views[key] = torch.as_tensor(_DevicePtr(self.slot_ptr(slot), shape, typestr), device="cuda")
+        return t
 
     def close(self):
         import torch.distributed as dist
         if self.base is None:
             return
+        self._views = {}
         if self.active:
             self.deactivate()
         self.ctx.sync()

@@ -148,7 +148,10 @@ int cs_set_threads(cs_context* ctx, int n_threads);
  *        the sliced strip: perlworlnoise.tga.import:24-27);
  * small: n^3 texels, 3 or 4 bytes per texel (worlnoise.bmp.import:24-27);
  * weather: w*h texels, 3 or 4 bytes per texel, row 0 = v 0 (weather.bmp.import:25, no mips).
- * The library copies the data and builds the box-filter mip chains of the two volumes. */
+ * The library copies the data and builds the box-filter mip chains of the two volumes.
+ * Sizes (CUDA backend): every edge a power of two (REPEAT addressing by mask); large <= 512^3, small <= 256^3, weather <=
+ * 8192^2 (the reference assets are 128^3 / 32^3 / 512^2).  Resident device footprint of the volumes: 8 x the RGBA8 texels
+ * (one 32-byte / 16-byte interpolation record per texel and mip level) + the texels themselves + a mipmapped CUDA array. */
 int cs_upload_textures(cs_context* ctx,
                        const uint8_t* large, int large_n, int large_ch,
                        const uint8_t* small, int small_n, int small_ch,

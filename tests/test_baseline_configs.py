@@ -132,13 +132,13 @@ def test_c5_adaptive_step_budget(cs, helpers, oracle_lib, product_lib, textures)
         o.render_rows_to(p, r, r + 1, buf.ctypes.data)
     frac, mx = rows_pass(helpers, adaptive[rows], buf[rows])
     assert frac >= FAST_TOL[2] and mx < 0.1, (frac, mx)
-    # with the early-out flag on top (the C5 mode): alpha bit-identical, rgb within 2 fp16 steps of the budget-only render
+    # with the early-out flag on top (the C5 mode): within 2 fp16 steps of the budget-only render (alpha: 1 step — it stops at
+    # T < 2^-12, i.e. right at the fp16 rounding midpoint below 1.0, on a handful of the 33 M pixels)
     g.set_march_config(P, cone, cs.MODE_FAST | cs.MODE_EARLY_OUT)
     g.render_frame(p)
     both = g.read_image()
-    assert (both[..., 3].view(np.uint16) == adaptive[..., 3].view(np.uint16)).all()
-    d = np.abs(both[..., :3].view(np.int16).astype(np.int32) - adaptive[..., :3].view(np.int16).astype(np.int32))
-    assert d.max() <= 2, d.max()
+    d = np.abs(both.view(np.int16).astype(np.int32) - adaptive.view(np.int16).astype(np.int32))
+    assert d[..., :3].max() <= 2 and d[..., 3].max() <= 1 and (d[..., 3] > 0).mean() < 1e-3, (d[..., :3].max(), d[..., 3].max(), (d[..., 3] > 0).mean())
     g.set_march_config(P, cone, cs.MODE_FAST)
     g.set_step_budget(0.0, 1)
     g.render_frame(p)

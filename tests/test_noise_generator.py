@@ -197,3 +197,32 @@ def test_gpu_render_from_generated_textures_matches_oracle(cs, oracle_lib, produ
     ok, mx = helpers.compare_images(imgs[0], imgs[1], 2e-3, 1e-2)
     assert 0.02 < imgs[1][..., 3].mean() < 0.98
     assert ok >= 0.998 and mx < 0.1, (ok, mx)  # the parity gate proper (>= 0.999 on the reference textures) is tests/test_gpu_parity.py
+
+
+@pytest.mark.gpu
+def test_gpu_larger_volumes_than_the_reference_assets(cs, oracle_lib, product_lib, helpers):
+    """The upload limit of round 1 (large <= 128^3, small <= 32^3) is gone: the generator's 256^3 / 64^3 / 1024^2 output
+    uploads, renders in every sampler mode and matches the oracle (which has no size limit)."""
+    g = product_lib.context(0)
+    tex = (g.generate_noise(cs.NOISE_LARGE, 256), g.generate_noise(cs.NOISE_SMALL, 64), g.generate_noise(cs.NOISE_WEATHER, 1024))
+    g.close()
+    W, H = 160, 80
+    o = helpers.prepared_context(oracle_lib, tex, W, H, threads=helpers.cpu_threads)
+    p = helpers.make_params(oracle_lib, W, H, coverage=0.35, time=3.0)
+    o.set_march_config(128, 6)
+    o.render_frame(p)
+    want = o.read_image()
+    assert 0.02 < want.astype(np.float32)[..., 3].mean() < 0.98
+    ctx = helpers.prepared_context(product_lib, tex, W, H)
+    for level in (0, 3, 8):  # mip chains product == oracle, 256 -> 1 is 9 levels
+        assert (ctx.read_volume_level(0, 256, level) == o.read_volume_level(0, 256, level)).all()
+    ctx.write_sky_lut(o.read_sky_lut())
+    for mode, tol in ((cs.MODE_STRICT, (1e-3, 2e-3, 0.999)), (cs.MODE_FAST, (2e-3, 1e-2, 0.998)), (cs.MODE_FAST | cs.MODE_TEX, (2e-3, 1e-2, 0.998))):
+        ctx.set_march_config(128, 6, mode)
+        ctx.render_frame(p)
+        ok, mx = helpers.compare_images(ctx.read_image(), want, tol[0], tol[1])
+        assert ok >= tol[2] and mx < 0.1, (mode, ok, mx)
+    ctx.close(); o.close()
+    with pytest.raises(cs.CloudSkyError):
+        big = product_lib.context(0)
+        big.upload_textures(np.zeros((24, 24, 24, 4), np.uint8), tex[1], tex[2])  # not a power of two: still refused, with a message

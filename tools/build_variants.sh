@@ -8,7 +8,7 @@ make -s >/dev/null
 mkdir -p ../../build/variants
 for spec in "$@"; do
   name="${spec%%:*}"; defs="${spec#*:}"
-  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -ftz=true $defs -c -o ../../build/variants/clouds_fast_$name.o clouds_fast.cu
-  nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../../build/variants/lib_$name.so context.o sky_resource.o composite.o lut_kernels.o clouds_strict.o noise_gen.o ../../build/variants/clouds_fast_$name.o assets.o host_logic.o
+  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -ftz=true -Xptxas -v $defs -c -o ../../build/variants/clouds_fast_$name.o clouds_fast.cu
+  nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../../build/variants/lib_$name.so context.o peer.o sky_resource.o composite.o lut_kernels.o clouds_strict.o noise_gen.o ../../build/variants/clouds_fast_$name.o assets.o host_logic.o
   echo "built build/variants/lib_$name.so ($defs)"
 done
