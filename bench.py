@@ -599,6 +599,11 @@ def run_ours(args):
         ms_tex = ctx.time_render_frame(params[0], 3, 10)
         extra["texture_unit_mode"] = {"march_ms": round(ms_tex, 4), "value_march_only": round(ray_steps_per_frame / ms_tex / 1e3, 1),
                                       "note": "opt-in mode flag (bench.py --sampler texture runs the whole bench in it); same parity tolerance as FAST, tests/test_gpu_parity.py"}
+        # Extra: the opt-in CS_MODE_HALF flag (the in-kernel filter in packed fp16 on the exact-integer records: 11-bit weights)
+        ctx.set_march_config(PRIMARY, CONE, cs.MODE_FAST | cs.MODE_HALF)
+        ms_half = ctx.time_render_frame(params[0], 3, 10)
+        extra["half_filter_mode"] = {"march_ms": round(ms_half, 4), "value_march_only": round(ray_steps_per_frame / ms_half / 1e3, 1),
+                                     "note": "opt-in mode flag: HFMA2 filter, no half->float conversions; same parity tolerance as FAST, tests/test_gpu_parity.py"}
         ctx.set_march_config(PRIMARY, CONE, base_mode)
 
     if not args.no_extra:

@@ -8,9 +8,9 @@ Import name: ``cloudsky_b200`` (see cloudsky_b200.py at the repo root; the direc
 from . import capi  # noqa: F401
 from .capi import (CloudParams, CloudSkyError, Context, Counters, FrameState, Library, NoiseParams, Sky, SkyFrame, SkySettings, View,  # noqa: F401
                    NOISE_LARGE, NOISE_SMALL, NOISE_WEATHER, TLUT_BRUNETON2017, TLUT_LINEAR,
-                   MODE_EARLY_OUT, MODE_FAST, MODE_STRICT, MODE_TEX, load_product)
+                   MODE_EARLY_OUT, MODE_FAST, MODE_HALF, MODE_STRICT, MODE_TEX, load_product)
 
 from .sky import CloudSky, DirectionalLight, SkyLUT, TransmittanceLUT  # noqa: F401,E402
 
 __all__ = ["CloudSky", "DirectionalLight", "SkyLUT", "TransmittanceLUT", "capi", "CloudParams", "CloudSkyError", "Context", "Counters", "FrameState", "Library", "NoiseParams", "NOISE_LARGE", "NOISE_SMALL", "NOISE_WEATHER", "TLUT_LINEAR", "TLUT_BRUNETON2017", "Sky", "SkyFrame", "SkySettings", "View",
-           "MODE_EARLY_OUT", "MODE_FAST", "MODE_STRICT", "MODE_TEX", "load_product"]
+           "MODE_EARLY_OUT", "MODE_FAST", "MODE_HALF", "MODE_STRICT", "MODE_TEX", "load_product"]

@@ -21,6 +21,7 @@ MODE_FAST = 0
 MODE_STRICT = 1
 MODE_EARLY_OUT = 2  # flag for MODE_FAST: stop a ray once T < 2^-12 (not reference behaviour)
 MODE_TEX = 4  # flag for MODE_FAST: the texture unit filters the noise volumes / weather map (8-bit filter weights)
+MODE_HALF = 8  # flag for MODE_FAST: the in-kernel filter runs in packed fp16 on the exact-integer records (11-bit weights)
 TRANSMITTANCE_W, TRANSMITTANCE_H = 256, 64  # transmittance_lut.gd:6
 SKY_LUT_W, SKY_LUT_H = 200, 100  # sky_lut.gd:4
 REF_PRIMARY_STEPS, REF_CONE_SAMPLES = 128, 6  # clouds.glsl:228, :186

@@ -50,9 +50,13 @@ void free_textures(cs_context* c) {
     for (auto& p : c->d_small) { if (p) cudaFree(p); p = nullptr; }
     for (auto& p : c->d_large_f) { if (p) cudaFree(p); p = nullptr; }
     for (auto& p : c->d_small_f) { if (p) cudaFree(p); p = nullptr; }
+    for (auto& p : c->d_large_h2) { if (p) cudaFree(p); p = nullptr; }
+    for (auto& p : c->d_small_h2) { if (p) cudaFree(p); p = nullptr; }
     if (c->d_weather) cudaFree(c->d_weather);
     if (c->d_weather_f) cudaFree(c->d_weather_f);
-    c->d_weather = nullptr; c->d_weather_f = nullptr;
+    if (c->d_weather_h2) cudaFree(c->d_weather_h2);
+    c->d_weather = nullptr; c->d_weather_f = nullptr; c->d_weather_h2 = nullptr;
+    c->have_h2 = false;
     if (c->t_large) cudaDestroyTextureObject(c->t_large);
     if (c->t_small) cudaDestroyTextureObject(c->t_small);
     if (c->t_weather) cudaDestroyTextureObject(c->t_weather);
@@ -250,6 +254,65 @@ bool pack_weather_h(const std::vector<uint8_t>& rgba, int w, int h, std::vector<
     return true;
 }
 
+// ---- CS_MODE_HALF records: the exact-integer coefficients again, arranged for packed-fp16 evaluation ----------------------
+// large   : 8 half2 (R_ci, K_ci), i = 0..7, with the constant terms centred (R_c0 - 128, K_c0 - 1020) so that the fp16 roundings
+//           of the running sums act on values half as large; the kernel adds the centres back in fp32 for free (FFMA).
+// small   : 4 half2 (c0 - 1020, c4), (c1, c5), (c2, c6), (c3, c7): the two z-halves of the polynomial side by side.
+// weather : 4 half2 (type_ci, coverage_ci), i = 0..3, constant terms centred by 128.
+template <class F>
+void trilinear_coeffs_int(F v, int n, int x, int y, int z, int* k) {
+    int x1 = (x + 1) % n, y1 = (y + 1) % n, z1 = (z + 1) % n;
+    int v000 = v(x, y, z), v100 = v(x1, y, z), v010 = v(x, y1, z), v110 = v(x1, y1, z);
+    int v001 = v(x, y, z1), v101 = v(x1, y, z1), v011 = v(x, y1, z1), v111 = v(x1, y1, z1);
+    k[0] = v000; k[1] = v100 - v000; k[2] = v010 - v000; k[3] = (v110 - v010) - k[1];
+    k[4] = v001 - v000; k[5] = (v101 - v001) - k[1]; k[6] = (v011 - v001) - k[2];
+    k[7] = ((v111 - v011) - (v101 - v001)) - k[3];
+}
+void pack_large_h2(const std::vector<uint8_t>& rgba, int n, std::vector<uint16_t>& out) {
+    out.resize((size_t)n * n * n * 16);
+    auto fr = [&](int x, int y, int z) { return (int)rgba[(((size_t)z * n + y) * n + x) * 4]; };
+    auto fk = [&](int x, int y, int z) { const uint8_t* t = &rgba[(((size_t)z * n + y) * n + x) * 4]; return 5 * t[1] + 2 * t[2] + t[3]; };
+    for (int z = 0; z < n; z++)
+        for (int y = 0; y < n; y++)
+            for (int x = 0; x < n; x++) {
+                int r[8], k[8];
+                trilinear_coeffs_int(fr, n, x, y, z, r);
+                trilinear_coeffs_int(fk, n, x, y, z, k);
+                r[0] -= 128; k[0] -= 1020;
+                uint16_t* o = &out[(((size_t)z * n + y) * n + x) * 16];
+                for (int i = 0; i < 8; i++) { o[2 * i] = half_bits_exact(r[i]); o[2 * i + 1] = half_bits_exact(k[i]); }
+            }
+}
+void pack_small_h2(const std::vector<uint8_t>& rgba, int n, std::vector<uint16_t>& out) {
+    out.resize((size_t)n * n * n * 8);
+    auto fh = [&](int x, int y, int z) { const uint8_t* t = &rgba[(((size_t)z * n + y) * n + x) * 4]; return 5 * t[0] + 2 * t[1] + t[2]; };
+    for (int z = 0; z < n; z++)
+        for (int y = 0; y < n; y++)
+            for (int x = 0; x < n; x++) {
+                int k[8];
+                trilinear_coeffs_int(fh, n, x, y, z, k);
+                k[0] -= 1020;
+                uint16_t* o = &out[(((size_t)z * n + y) * n + x) * 8];
+                for (int i = 0; i < 4; i++) { o[2 * i] = half_bits_exact(k[i]); o[2 * i + 1] = half_bits_exact(k[i + 4]); }
+            }
+}
+void pack_weather_h2(const std::vector<uint8_t>& rgba, int w, int h, std::vector<uint16_t>& out) {
+    out.resize((size_t)w * h * 8);
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            int x1 = (x + 1) % w, y1 = (y + 1) % h;
+            int c[2][4];
+            for (int ch = 0; ch < 2; ch++) {
+                int k = ch == 0 ? 0 : 2;
+                int v00 = rgba[((size_t)y * w + x) * 4 + k], v10 = rgba[((size_t)y * w + x1) * 4 + k];
+                int v01 = rgba[((size_t)y1 * w + x) * 4 + k], v11 = rgba[((size_t)y1 * w + x1) * 4 + k];
+                c[ch][0] = v00 - 128; c[ch][1] = v10 - v00; c[ch][2] = v01 - v00; c[ch][3] = (v11 - v01) - (v10 - v00);
+            }
+            uint16_t* o = &out[((size_t)y * w + x) * 8];
+            for (int i = 0; i < 4; i++) { o[2 * i] = half_bits_exact(c[0][i]); o[2 * i + 1] = half_bits_exact(c[1][i]); }
+        }
+}
+
 int ilog2(int v) { int s = 0; while ((1 << s) < v) s++; return s; }
 
 int upload_levels(cs_context* c, const std::vector<uint8_t>& large0, int ln, const std::vector<uint8_t>& small0, int sn,
@@ -272,6 +335,7 @@ int upload_levels(cs_context* c, const std::vector<uint8_t>& large0, int ln, con
     c->large_n = ln; c->large_levels = (int)c->h_large.size();
     c->small_n = sn; c->small_levels = (int)c->h_small.size();
     c->weather_w = ww; c->weather_h = wh;
+    c->h_weather = weather;
     c->weather_type_hi = 1;
     for (size_t i = 0; i < weather.size(); i += 4) if (weather[i] < 128) { c->weather_type_hi = 0; break; }
     for (int l = 0; l < c->large_levels; l++) {
@@ -318,6 +382,26 @@ int upload_levels(cs_context* c, const std::vector<uint8_t>& large0, int ln, con
     return CS_OK;
 }
 
+// CS_MODE_HALF: build the half2 records on first use (another 8 x the texel bytes; only contexts that ask for the mode pay for it).
+int ensure_half2_records(cs_context* c) {
+    if (c->have_h2) return CS_OK;
+    if (!c->have_tex) return fail(c, CS_ERR_NOT_READY, "input textures not uploaded");
+    if (c->records_half != 7) return fail(c, CS_ERR_UNSUPPORTED, "CS_MODE_HALF needs textures whose interpolation coefficients are exact in fp16");
+    int r = bind(c);
+    if (r) return r;
+    auto put = [&](float** dst, const std::vector<uint16_t>& v) -> cudaError_t {
+        cudaError_t e = cudaMalloc(dst, v.size() * 2);
+        return e != cudaSuccess ? e : cudaMemcpy(*dst, v.data(), v.size() * 2, cudaMemcpyHostToDevice);
+    };
+    std::vector<uint16_t> pk;
+    for (int l = 0; l < c->large_levels; l++) { pack_large_h2(c->h_large[l], c->large_n >> l, pk); CU(put(&c->d_large_h2[l], pk)); }
+    for (int l = 0; l < c->small_levels; l++) { pack_small_h2(c->h_small[l], c->small_n >> l, pk); CU(put(&c->d_small_h2[l], pk)); }
+    pack_weather_h2(c->h_weather, c->weather_w, c->weather_h, pk);
+    CU(put(&c->d_weather_h2, pk));
+    c->have_h2 = true;
+    return CS_OK;
+}
+
 // img_w/img_h > 0: `out` is a caller-owned image of that size (a cs_sky's own textures); otherwise the context's image size.
 int make_launch(cs_context* c, const cs_cloud_params* P, int x0, int y0, int x1, int y1, uint16_t* out, const uint16_t* sky_lut, CloudLaunch& L,
                 int img_w = 0, int img_h = 0) {
@@ -340,13 +424,18 @@ int make_launch(cs_context* c, const cs_cloud_params* P, int x0, int y0, int x1,
     L.large_n = c->large_n; L.large_levels = c->large_levels;
     L.small_n = c->small_n; L.small_levels = c->small_levels;
     L.weather_w = c->weather_w; L.weather_h = c->weather_h;
-    for (int l = 0; l < kMaxLargeLevels; l++) { L.large[l] = c->d_large[l]; L.large_f[l] = c->d_large_f[l]; }
-    for (int l = 0; l < kMaxSmallLevels; l++) { L.small[l] = c->d_small[l]; L.small_f[l] = c->d_small_f[l]; }
-    L.weather = c->d_weather; L.weather_f = c->d_weather_f;
+    const bool half2 = (c->mode != CS_MODE_STRICT) && (c->mode & CS_MODE_HALF);
+    if (half2 && !c->have_h2) {  // textures were (re)uploaded after the mode was set
+        int r = ensure_half2_records(c);
+        if (r) return r;
+    }
+    for (int l = 0; l < kMaxLargeLevels; l++) { L.large[l] = c->d_large[l]; L.large_f[l] = half2 ? c->d_large_h2[l] : c->d_large_f[l]; }
+    for (int l = 0; l < kMaxSmallLevels; l++) { L.small[l] = c->d_small[l]; L.small_f[l] = half2 ? c->d_small_h2[l] : c->d_small_f[l]; }
+    L.weather = c->d_weather; L.weather_f = half2 ? c->d_weather_h2 : c->d_weather_f;
     L.large_shift = ilog2(c->large_n); L.small_shift = ilog2(c->small_n);
     L.weather_shx = ilog2(c->weather_w); L.weather_shy = ilog2(c->weather_h);
     L.weather_type_hi = c->weather_type_hi;
-    L.records_half = c->records_half;
+    L.records_half = half2 ? 16 : c->records_half;
     // texels per metre at level 0 (exact: power-of-two edge times the shader's texture scale, clouds.glsl:117,132)
     L.large_fn0 = (float)c->large_n * 0.00008f; L.small_fn0 = (float)c->small_n * 0.001f;
     L.weather_fw = (float)c->weather_w; L.weather_fh = (float)c->weather_h;
@@ -357,6 +446,7 @@ int make_launch(cs_context* c, const cs_cloud_params* P, int x0, int y0, int x1,
         const uint8_t* t = c->h_small[c->small_levels - 1].data();
         L.small_tail_level = c->small_levels - 1;
         if (c->mode & CS_MODE_TEX) L.small_tail_value = fmaf(un8(t[0]), 0.625f, fmaf(un8(t[1]), 0.25f, un8(t[2]) * 0.125f));
+        else if (half2) L.small_tail_value = fmaf((float)(5 * t[0] + 2 * t[1] + t[2] - 1020), 1.0f / 2040.0f, 0.5f);
         else if (c->records_half & 2) L.small_tail_value = (float)(5 * t[0] + 2 * t[1] + t[2]) * (1.0f / 2040.0f);
         else L.small_tail_value = un8(t[0]) * 0.625f + un8(t[1]) * 0.25f + un8(t[2]) * 0.125f;
     }
@@ -680,8 +770,13 @@ int cs_resize(cs_context* c, int w, int h) {
 }
 int cs_set_march_config(cs_context* c, int p, int cone, int mode) {
     if (!c) return CS_ERR_INVALID;
-    if (p < 1 || p > 4096 || cone < 0 || cone > 64 || (mode != CS_MODE_STRICT && (mode & ~(CS_MODE_EARLY_OUT | CS_MODE_TEX)) != CS_MODE_FAST))
-        return fail(c, CS_ERR_INVALID, "cs_set_march_config: primary_steps in [1,4096], cone_samples in [0,64], mode STRICT, or FAST optionally | EARLY_OUT | TEX");
+    if (p < 1 || p > 4096 || cone < 0 || cone > 64 || (mode != CS_MODE_STRICT && (mode & ~(CS_MODE_EARLY_OUT | CS_MODE_TEX | CS_MODE_HALF)) != CS_MODE_FAST) ||
+        (mode != CS_MODE_STRICT && (mode & CS_MODE_TEX) && (mode & CS_MODE_HALF)))
+        return fail(c, CS_ERR_INVALID, "cs_set_march_config: primary_steps in [1,4096], cone_samples in [0,64], mode STRICT, or FAST optionally | EARLY_OUT | one of TEX, HALF");
+    if (mode != CS_MODE_STRICT && (mode & CS_MODE_HALF)) {
+        int r = ensure_half2_records(c);
+        if (r) return r;
+    }
     c->primary_steps = p; c->cone_samples = cone; c->mode = mode;
     return CS_OK;
 }
@@ -807,7 +902,7 @@ int cs_render_sun_batch_to(cs_context* c, const cs_cloud_params* P, const float*
     const size_t image_px = (size_t)c->W * c->H;
     // CS_MODE_FAST with the record sampler: up to kMaxSunBatch suns share one march (clouds_fast_sunbatch_kernel) — the primary
     // loop is sun-independent.  Other modes, instrumented runs and step counts beyond the tables: one launch per sun.
-    const bool batched = c->mode == CS_MODE_FAST && !c->counters_on && !c->timing_on && c->cone_samples + 1 <= 16 && n > 1 && c->have_tlut && c->sun_batching;
+    const bool batched = c->mode == CS_MODE_FAST /* no flags: the batch kernel exists for the fp32-filter record formats only */ && !c->counters_on && !c->timing_on && c->cone_samples + 1 <= 16 && n > 1 && c->have_tlut && c->sun_batching;
     int i = 0;
     while (i < n) {
         const int k = batched ? std::min(n - i, (int)kMaxSunBatch) : 1;

@@ -24,6 +24,12 @@ struct cs_context {
     float* d_large_f[cs::kMaxLargeLevels] = {};
     float* d_small_f[cs::kMaxSmallLevels] = {};
     float* d_weather_f = nullptr;
+    // CS_MODE_HALF: the same exact-integer fp16 coefficients, centred and interleaved as half2 pairs (built on first use)
+    float* d_large_h2[cs::kMaxLargeLevels] = {};
+    float* d_small_h2[cs::kMaxSmallLevels] = {};
+    float* d_weather_h2 = nullptr;
+    bool have_h2 = false;
+    std::vector<uint8_t> h_weather;  // host copy of the RGBA8 weather map (repack)
     // CS_MODE_TEX: the same mip chains as CUDA mipmapped arrays behind texture objects
     cudaMipmappedArray_t a_large = nullptr, a_small = nullptr;
     cudaArray_t a_weather = nullptr;

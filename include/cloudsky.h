@@ -121,6 +121,13 @@ typedef struct cs_counters {
  * interpolates with 8-bit fixed-point weights, so results differ from the fp32-filtered oracle by up to ~3e-3 absolute
  * (inside the FAST parity tolerance, tests/test_gpu_parity.py); texel values and mip chains are identical. */
 #define CS_MODE_TEX 4
+/* Optional flag for CS_MODE_FAST (mode = CS_MODE_FAST | CS_MODE_HALF [| CS_MODE_EARLY_OUT]; not together with CS_MODE_TEX): the
+ * in-kernel trilinear / bilinear filter is evaluated in packed fp16 (HFMA2) directly on the exact-integer coefficient records —
+ * no half->float conversions, two channels per instruction.  Filter weights and the three lerp levels round to 11 bits
+ * (finer than the texture unit's 8-bit weights, coarser than the fp32 filter of plain CS_MODE_FAST); texel values and mip
+ * chains are identical.  Same parity tolerance as CS_MODE_FAST (tests/test_gpu_parity.py).  Needs textures whose
+ * interpolation coefficients are exact in fp16 (true for the reference's; CS_ERR_UNSUPPORTED otherwise). */
+#define CS_MODE_HALF 8
 
 /* ---- lifetime -------------------------------------------------------------------------- */
 

@@ -23,7 +23,7 @@ def main():
         p = make_params(lib, W, H, **kw)
         o.build_sky_lut(tuple(p.light_direction)); o.render_frame(p); ref = o.read_image().astype(np.float32)[1:, 1:]
         g.write_sky_lut(o.read_sky_lut())
-        for mode, mname in ((cs.MODE_STRICT, "strict"), (cs.MODE_FAST, "fast"), (cs.MODE_FAST | cs.MODE_TEX, "fast+tex")):
+        for mode, mname in ((cs.MODE_STRICT, "strict"), (cs.MODE_FAST, "fast"), (cs.MODE_FAST | cs.MODE_TEX, "fast+tex"), (cs.MODE_FAST | cs.MODE_HALF, "fast+half")):
             g.set_march_config(128, 6, mode); g.render_frame(p)
             d = np.abs(g.read_image().astype(np.float32)[1:, 1:] - ref)
             r = dict(case=name, mode=mname,

@@ -40,7 +40,7 @@ def test_c2_full_frame_with_lut_builds(cs, helpers, oracle_lib, product_lib, tex
     o.set_march_config(P, cone)
     o.render_frame(p)
     want = o.read_image()
-    for mode in (cs.MODE_FAST, cs.MODE_FAST | cs.MODE_TEX):
+    for mode in (cs.MODE_FAST, cs.MODE_FAST | cs.MODE_TEX, cs.MODE_FAST | cs.MODE_HALF):
         g.set_march_config(P, cone, mode)
         g.render_frame(p)
         frac, mx = helpers.compare_images(g.read_image(), want, FAST_TOL[0], FAST_TOL[1])
@@ -48,13 +48,13 @@ def test_c2_full_frame_with_lut_builds(cs, helpers, oracle_lib, product_lib, tex
     g.close(); o.close()
 
 
-@pytest.mark.parametrize("mode", ["fast", "tex"])
+@pytest.mark.parametrize("mode", ["fast", "tex", "half"])
 def test_c3_headline_frames_as_bench_renders_them(cs, helpers, oracle_lib, product_lib, textures, mode):
     W, H = bench.W, bench.H
     sun = (0.0, 1.0, 0.0)
     g = helpers.prepared_context(product_lib, textures, W, H, sun=sun)
     o = helpers.prepared_context(oracle_lib, textures, W, H, sun=sun, threads=helpers.cpu_threads)
-    g.set_march_config(bench.PRIMARY, bench.CONE, cs.MODE_FAST | (cs.MODE_TEX if mode == "tex" else 0))
+    g.set_march_config(bench.PRIMARY, bench.CONE, cs.MODE_FAST | {"fast": 0, "tex": cs.MODE_TEX, "half": cs.MODE_HALF}[mode])
     o.set_march_config(bench.PRIMARY, bench.CONE)
     rows = list(range(9, H, 64))  # 16 rows
     buf = np.zeros((H, W, 4), np.float16)

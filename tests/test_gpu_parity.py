@@ -60,7 +60,7 @@ CASES = [
 
 
 @pytest.mark.parametrize("case", CASES)
-@pytest.mark.parametrize("mode", ["strict", "fast", "tex"])
+@pytest.mark.parametrize("mode", ["strict", "fast", "tex", "half"])
 def test_clouds_match_oracle(cs, pair, helpers, oracle_lib, product_lib, case, mode):
     o, g, W, H = pair
     po = helpers.make_params(oracle_lib, W, H, **case)
@@ -71,7 +71,7 @@ def test_clouds_match_oracle(cs, pair, helpers, oracle_lib, product_lib, case, m
     o.build_sky_lut(sun)
     o.render_frame(po)
     ref = o.read_image()
-    g.set_march_config(128, 6, {"strict": cs.MODE_STRICT, "fast": cs.MODE_FAST, "tex": cs.MODE_FAST | cs.MODE_TEX}[mode])
+    g.set_march_config(128, 6, {"strict": cs.MODE_STRICT, "fast": cs.MODE_FAST, "tex": cs.MODE_FAST | cs.MODE_TEX, "half": cs.MODE_FAST | cs.MODE_HALF}[mode])
     g.write_sky_lut(o.read_sky_lut())  # identical LUT texels on both sides isolates the march
     g.render_frame(pg)
     out = g.read_image()
@@ -237,11 +237,11 @@ def test_counters_match_oracle(cs, pair, helpers, oracle_lib, product_lib):
     assert abs(kg["density_evals"] - ko["density_evals"]) <= 1e-3 * ko["density_evals"]
 
 
-@pytest.mark.parametrize("mode", ["strict", "fast", "tex"])
+@pytest.mark.parametrize("mode", ["strict", "fast", "tex", "half"])
 def test_tile_invariance(cs, pair, helpers, product_lib, mode):
     """1, 4 and 64 tiles give bit-identical textures (cloud_sky.gd:156-161 tile walk)."""
     _, g, W, H = pair
-    g.set_march_config(128, 6, {"strict": cs.MODE_STRICT, "fast": cs.MODE_FAST, "tex": cs.MODE_FAST | cs.MODE_TEX}[mode])
+    g.set_march_config(128, 6, {"strict": cs.MODE_STRICT, "fast": cs.MODE_FAST, "tex": cs.MODE_FAST | cs.MODE_TEX, "half": cs.MODE_FAST | cs.MODE_HALF}[mode])
     g.build_sky_lut((0, 1, 0))
     p = helpers.make_params(product_lib, W, H, time=12.0)
     g.render_frame(p)

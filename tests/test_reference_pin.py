@@ -173,9 +173,10 @@ def test_gpu_lut_kernels_match_reference_golden(cs, product_lib, textures, helpe
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", ["strict", "fast", "tex"])
+@pytest.mark.parametrize("mode", ["strict", "fast", "tex", "half"])
 def test_gpu_march_matches_reference_golden(cs, product_lib, textures, helpers, gold, mode):
-    m, tol = {"strict": (cs.MODE_STRICT, STRICT_TOL), "fast": (cs.MODE_FAST, FAST_TOL), "tex": (cs.MODE_FAST | cs.MODE_TEX, FAST_TOL)}[mode]
+    m, tol = {"strict": (cs.MODE_STRICT, STRICT_TOL), "fast": (cs.MODE_FAST, FAST_TOL), "tex": (cs.MODE_FAST | cs.MODE_TEX, FAST_TOL),
+              "half": (cs.MODE_FAST | cs.MODE_HALF, FAST_TOL)}[mode]
     ctx = helpers.prepared_context(product_lib, textures, W, H)
     ctx.set_march_config(128, 6, m)
     for name in CASES:
@@ -188,12 +189,12 @@ def test_gpu_march_matches_reference_golden(cs, product_lib, textures, helpers, 
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", ["fast", "tex"])
+@pytest.mark.parametrize("mode", ["fast", "tex", "half"])
 def test_gpu_bench_frames_match_reference_golden_rows(cs, product_lib, textures, helpers, gold, mode):
     """The 2048x1024 frames bench.py renders (k = 0 and k = 15 of the wind animation), at the reference's 6+1 light
     samples, against 16 rows of the compiled reference."""
     ctx = helpers.prepared_context(product_lib, textures, C3_W, C3_H)
-    ctx.set_march_config(128, 6, cs.MODE_FAST | (cs.MODE_TEX if mode == "tex" else 0))
+    ctx.set_march_config(128, 6, cs.MODE_FAST | {"fast": 0, "tex": cs.MODE_TEX, "half": cs.MODE_HALF}[mode])
     ctx.write_sky_lut(gold["c3_sky"])
     rows = gold["c3_rows"]
     for k in (0, 15):
