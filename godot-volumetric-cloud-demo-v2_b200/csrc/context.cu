@@ -461,6 +461,8 @@ int make_launch(cs_context* c, const cs_cloud_params* P, int x0, int y0, int x1,
     if (c->n_mirrors > 0) {
         const uint8_t* o = reinterpret_cast<const uint8_t*>(out);
         if (o >= c->mirror_base && o < c->mirror_base + c->mirror_bytes) {  // `out` lies in the registered range: replicate at the same offset
+            if ((size_t)(o - c->mirror_base) + (size_t)IW * IH * 8 > c->mirror_bytes)
+                return fail(c, CS_ERR_INVALID, "output image starts inside the range registered with cs_set_output_mirrors but does not fit in it");
             L.n_mirrors = c->n_mirrors;
             for (int m = 0; m < c->n_mirrors; m++) L.mirror[m] = reinterpret_cast<uint16_t*>(c->mirror_peer[m] + (o - c->mirror_base));
         }
@@ -930,6 +932,8 @@ int cs_render_sun_batch_to(cs_context* c, const cs_cloud_params* P, const float*
             }
             L.frame_consts = c->d_frame_consts;
             L.n_suns = k; L.sun_stride_px = image_px;
+            if (L.n_mirrors > 0 && (size_t)(reinterpret_cast<const uint8_t*>(L.out) - c->mirror_base) + (size_t)k * image_px * 8 > c->mirror_bytes)
+                return fail(c, CS_ERR_INVALID, "cs_render_sun_batch_to: the batch does not fit in the range registered with cs_set_output_mirrors");
             if (!launch_clouds_fast_sunbatch(L, c->stream)) return fail(c, CS_ERR_INVALID, "cs_render_sun_batch_to: no batch kernel for this configuration");
             CU(cudaGetLastError());
         }
