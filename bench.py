@@ -662,8 +662,6 @@ def run_extras(cs, sharding, lib, ctx, torch, dist, world, rank, allmax, allgath
     stream = torch.cuda.current_stream()
     use_peer = world == 1 or gather == "peer"
     R = sharding.ShardedRenderer(ctx, W, H, device="cuda", gather="peer" if use_peer else "nccl")
-    if peer is not None:
-        peer.deactivate()
 
     def timed(fn, iters, warm=2, kernel_timing=True):
         """-> (ms per call, max over ranks; this rank's kernel ms per call; last result).  kernel_timing=False: the sun-batch kernel

@@ -80,11 +80,12 @@ class _DevicePtr:
 class PeerBuffers:
     """`slots` copies-in-time of a gathered buffer of `slot_bytes`, replicated on every rank and mapped into every rank.
 
-    own[s]    : device pointer of slot s in this rank's copy
     After activate(), any march dispatch that writes into this rank's copy also writes the same pixels, at the same offset,
     into every peer's copy (cs_set_output_mirrors); barrier() then makes the copy complete on this rank's stream.
     Two slots used alternately make back-to-back steps safe: a peer starts overwriting slot s (step k+2) only after this rank
-    published step k+1, which is stream-ordered after whatever this rank queued to consume step k."""
+    published step k+1, which is stream-ordered after whatever this rank queued to consume step k.
+    One registered range per context: activating a PeerBuffers deactivates the one that was active before.  Tensors returned
+    by tensor() alias library memory and die with close()."""
 
     def __init__(self, ctx, slot_bytes: int, slots: int = 2, group=None):
         import torch.distributed as dist
@@ -111,11 +112,17 @@ class PeerBuffers:
         self._views = {}
 
     def activate(self):
+        prev = getattr(self.ctx, "_active_peer_buffers", None)
+        if prev is not None and prev is not self:
+            prev.active = False  # cs_set_output_mirrors replaces the registered range
         self.ctx.set_output_mirrors(self.base, self.nbytes, [b for k, b in enumerate(self.bases) if k != self.rank])
+        self.ctx._active_peer_buffers = self
         self.active = True
 
     def deactivate(self):
-        self.ctx.set_output_mirrors(0, 0, [])
+        if self.active:
+            self.ctx.set_output_mirrors(0, 0, [])
+            self.ctx._active_peer_buffers = None
         self.active = False
 
     def slot_ptr(self, slot: int) -> int:
@@ -241,9 +248,6 @@ class ShardedRenderer:
         if pb is None:
             pb = self._peer[slot_bytes] = PeerBuffers(self.ctx, slot_bytes, 2, self.group)
         if not pb.active:
-            for other in self._peer.values():
-                if other.active:
-                    other.deactivate()
             pb.activate()
         self._step += 1
         return pb, self._step & 1
