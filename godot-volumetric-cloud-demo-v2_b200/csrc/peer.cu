@@ -8,6 +8,7 @@
 // to each peer's flag array and waits until every peer has published the same.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <cstring>
 
 #include "cs_context.h"
@@ -125,7 +126,9 @@ int cs_peer_barrier(cs_context* c, int rank, int world, void* const* flag_arrays
     if (c->peer_watchdog_cycles == 0) {  // queried once: device-attribute calls take a driver-wide lock (milliseconds with 8 busy processes)
         int khz = 0;
         cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, c->device);
-        c->peer_watchdog_cycles = (long long)(khz > 0 ? khz : 2000000) * 1000ll * 20ll;  // ~20 s of SM clocks
+        long long ms = 20000;  // ~20 s of SM clocks; CLOUDSKY_PEER_WATCHDOG_MS overrides (tests use a short one)
+        if (const char* e = getenv("CLOUDSKY_PEER_WATCHDOG_MS")) { long long v = atoll(e); if (v > 0) ms = v; }
+        c->peer_watchdog_cycles = (long long)(khz > 0 ? khz : 2000000) * ms;
     }
     const long long watchdog = c->peer_watchdog_cycles;
     peer_barrier_kernel<<<1, 32, 0, c->stream>>>(f, rank, world, epoch, c->d_peer_err, watchdog);

@@ -140,3 +140,22 @@ def test_peer_gather_world_one(cs, product_lib, textures, helpers):
     ctx.peer_check()
     r.close()
     ctx.close()
+
+
+def test_peer_barrier_watchdog_reports_a_missing_peer(cs, product_lib, monkeypatch):
+    """A rank that never arrives must not hang the GPU: the barrier kernel gives up after the watchdog time and
+    cs_peer_check turns that into an error (here: a 'world' of 2 whose second flag array nobody ever writes)."""
+    monkeypatch.setenv("CLOUDSKY_PEER_WATCHDOG_MS", "150")
+    ctx = product_lib.context(0)
+    mine, _ = ctx.peer_alloc(256)
+    absent, _ = ctx.peer_alloc(256)
+    ctx.peer_barrier(0, 2, [mine, absent], 1)
+    with pytest.raises(cs.CloudSkyError) as e:
+        ctx.peer_check()
+    assert e.value.code == 5 and "did not arrive" in str(e.value)
+    ctx.peer_check()  # the error is reported once
+    ctx.peer_barrier(0, 1, [mine], 2)  # and the context keeps working
+    ctx.sync()
+    ctx.peer_check()
+    ctx.peer_free(mine); ctx.peer_free(absent)
+    ctx.close()
