@@ -457,6 +457,8 @@ struct CloudCtx {
     // steps(dir) = clamp(ceil(shell length / budget_len), budget_min, primary_steps); 0 = the reference's fixed count
     float budget_len = 0.0f;
     int budget_min = 1;
+    int study_variant = 0;  // cso_set_study_variant: bit 0 = light-sample positions as p + (cumulative offset) in ONE add, the way the fast CUDA
+                            // kernel's per-CTA tables do, instead of the shader's sequential lp += step (clouds.glsl:187) — a noise-source study
 };
 struct Tally { uint64_t px = 0, steps = 0, lit = 0, evals = 0; };
 
@@ -624,9 +626,11 @@ V4 march(const CloudCtx& c, V3 pos, V3 /*end*/, V3 dir, int depth, Tally& tl) {
         if (t > 0.0f) {
             tl.lit++;
             float lheight_fraction = 0.0f;
+            V3 cum = {0.0f, 0.0f, 0.0f};
             for (int j = 0; j < c.cone_samples; j++) {  // 6 in the reference (:186)
                 V3 step = (ldir + RANDOM_VECTORS[j % 6] * (float)j) * lss;
-                lp = lp + step;
+                if (c.study_variant & 1) { cum = cum + step; lp = p + cum; }
+                else lp = lp + step;
                 lheight_fraction = GetHeightFractionForPoint(length3(lp));
                 V3 lweather = sample_weather(*c.weather, {lp.x * weather_scale + 0.5f + weather_pos.x, lp.z * weather_scale + 0.5f + weather_pos.y});
                 lt = density(c, lp, lweather, (float)j, tl);
@@ -722,6 +726,7 @@ struct cs_context {
     float hier_margin = 0.0f;
     float budget_len = 0.0f;
     int budget_min = 1;
+    int study_variant = 0;
     cs_counters counters{};
 };
 
@@ -841,7 +846,7 @@ static int render_region(cs_context* c, const cs_cloud_params* P, int x0, int y0
     x0 = std::max(x0, 0); y0 = std::max(y0, 0); x1 = std::min(x1, c->W); y1 = std::min(y1, c->H);
     CloudCtx cc{&c->large, &c->small, &c->weather, c->skylut.data(), *P, c->primary_steps, c->cone_samples};
     cc.hier_stride = c->hier_stride; cc.hier_margin = c->hier_margin; cc.hier_lod_bias = c->hier_lod_bias;
-    cc.budget_len = c->budget_len; cc.budget_min = c->budget_min;
+    cc.budget_len = c->budget_len; cc.budget_min = c->budget_min; cc.study_variant = c->study_variant;
     std::vector<Tally> tl((size_t)std::max(c->threads, 1));
     parallel_rows(c->threads, std::max(y1 - y0, 0), [&](int r, int t) {
         int y = y0 + r;
@@ -1383,6 +1388,7 @@ int cso_set_hierarchical(cs_context* c, int stride, float margin, int lod_bias) 
     if (!c || stride < 0 || stride == 1 || stride > 32 || !(margin >= 0.0f) || margin > 1.0f || lod_bias < -8 || lod_bias > 8) return CS_ERR_INVALID;
     c->hier_stride = stride; c->hier_margin = margin; c->hier_lod_bias = lod_bias; return CS_OK;
 }
+int cso_set_study_variant(cs_context* c, int flags) { if (!c) return CS_ERR_INVALID; c->study_variant = flags; return CS_OK; }
 float cso_intersect_sphere(const float dir[3], float r) { return intersectSphere({0.0f, g_radius, 0.0f}, {dir[0], dir[1], dir[2]}, r); }
 float cso_hash(const float p[3]) { return hash3({p[0], p[1], p[2]}); }
 float cso_henyey_greenstein(float c, float g) { return henyey_greenstein(c, g); }

@@ -84,6 +84,13 @@ def test_clouds_match_oracle(cs, pair, helpers, oracle_lib, product_lib, case, m
     else:
         frac, mx = helpers.compare_images(out, ref, 2e-3, 1e-2)
         assert frac >= 0.999, (frac, mx)
+        if mode == "fast":
+            # Since round 2 the fast kernel follows the reference's rounding trajectory (ray setup, light-sample offsets and the
+            # quantised fp32 length() in the shader's own roundings): it holds the STRICT tolerance too, and nearly all pixels are
+            # bit-identical to the oracle (measured 97.5-99.9 %, max abs error 4.9e-4).
+            tight, mx_t = helpers.compare_images(out, ref, 1e-3, 2e-3)
+            same = (out[1:, 1:].view(np.uint16) == ref[1:, 1:].view(np.uint16)).all(-1).mean()
+            assert tight >= 0.9995 and mx_t < 5e-3 and same >= 0.93, (tight, mx_t, same)
     assert mx < 0.1
 
 
@@ -470,3 +477,35 @@ def test_error_behaviour(cs, product_lib, small_textures, helpers):
     ctx.dispatch_clouds(q, 4, 4)
     ctx.sync()
     ctx.close()
+
+
+def test_random_parameter_sets_all_sampler_modes(cs, pair, helpers, oracle_lib, product_lib):
+    """Seeded fuzz over the push-constant surface (the same generator family as tests/test_reference_pin.py's CPU fuzz, where the
+    oracle is shown bit-identical to the compiled reference): every sampler mode stays inside its gate on every case."""
+    o, g, W, H = pair
+    rng = np.random.default_rng(777)
+    worst = {}
+    for it in range(6):
+        el = rng.uniform(0.05, 1.0) if it % 3 else rng.uniform(-0.02, 0.06)
+        az = rng.uniform(0, 2 * np.pi)
+        c = np.sqrt(max(0.0, 1 - el * el))
+        kw = dict(sun=(np.cos(az) * c, el, np.sin(az) * c), coverage=float(rng.uniform(0.1, 1.0)), density=float(rng.uniform(0.02, 0.15)),
+                  time=float(rng.uniform(0.0, 300.0)), wind_direction=float(rng.uniform(0, 6.28)), wind_speed=float(rng.uniform(0, 6)),
+                  energy=float(rng.uniform(0.3, 3.0)), color=tuple(float(v) for v in rng.uniform(0.3, 1.0, 3)))
+        po = helpers.make_params(oracle_lib, W, H, **kw)
+        pg = helpers.make_params(product_lib, W, H, **kw)
+        assert bytes(po) == bytes(pg)
+        o.set_march_config(128, 6)
+        o.build_sky_lut(tuple(po.light_direction))
+        o.render_frame(po)
+        ref = o.read_image()
+        g.write_sky_lut(o.read_sky_lut())
+        for name, mode, tol in (("strict", cs.MODE_STRICT, (1e-3, 2e-3)), ("fast", cs.MODE_FAST, (2e-3, 1e-2)), ("tex", cs.MODE_FAST | cs.MODE_TEX, (2e-3, 1e-2)),
+                                ("half", cs.MODE_FAST | cs.MODE_HALF, (2e-3, 1e-2))):
+            g.set_march_config(128, 6, mode)
+            g.render_frame(pg)
+            frac, mx = helpers.compare_images(g.read_image(), ref, tol[0], tol[1])
+            worst[name] = min(worst.get(name, 1.0), frac)
+            assert frac >= 0.999 and mx < 0.1, (it, name, frac, mx, kw)
+    print("worst pass fractions:", worst)
+    g.set_march_config(128, 6, cs.MODE_FAST)

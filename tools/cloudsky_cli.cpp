@@ -6,7 +6,8 @@
 // PPM preview.  It plays the role of cloud_sky.gd's _update_per_frame_data + _render_process
 // (cloud_sky.gd:165-187,234-248) for a headless caller.  --procedural SEED LARGE_N SMALL_N WEATHER_N replaces the bitmaps by
 // noise synthesised on the device (cs_generate_noise, the reference README's TODO 3); --bruneton selects the Bruneton 2017
-// transmittance-LUT mapping (README TODO 2); --flags N ORs march-mode flags (2 early out, 4 texture unit) into the mode.
+// transmittance-LUT mapping (README TODO 2); --flags N ORs march-mode flags (2 early out, 4 texture unit, 8 packed-fp16 filter) into the
+// mode; --budget LEN MIN sets the adaptive per-direction step count (cs_set_step_budget; clouds.glsl:227's "fewer steps" hint).
 #include <dlfcn.h>
 
 #include <chrono>
@@ -35,6 +36,8 @@ int main(int argc, char** argv) {
     float sun[3] = {0.0f, 1.0f, 0.0f}, time_s = 0.0f, coverage = -1.0f, density = -1.0f, wind_dir = 0.0f, wind_speed = 1.0f;
     int procedural = 0, gen_n[3] = {128, 32, 512}, tlut_mapping = CS_TLUT_LINEAR, flags = 0;
     unsigned seed = 1;
+    float budget_len = 0.0f;
+    int budget_min = 1;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         auto next = [&]() -> const char* { return i + 1 < argc ? argv[++i] : ""; };
@@ -53,12 +56,13 @@ int main(int argc, char** argv) {
         else if (a == "--procedural") { procedural = 1; seed = (unsigned)strtoul(next(), nullptr, 0); for (int k = 0; k < 3; k++) gen_n[k] = atoi(next()); }
         else if (a == "--bruneton") tlut_mapping = CS_TLUT_BRUNETON2017;
         else if (a == "--flags") flags = atoi(next());
+        else if (a == "--budget") { budget_len = (float)atof(next()); budget_min = atoi(next()); }
         else if (a == "--out") out_f16 = next();
         else if (a == "--ppm") out_ppm = next();
         else {
             printf("usage: cloudsky_cli [--lib so] [--assets dir] [--size W H] [--steps P cone] [--strict] [--device n]\n"
                    "       [--sun x y z] [--time s] [--coverage c] [--density d] [--wind dir_rad speed] [--iters n] [--out img.f16] [--ppm img.ppm]\n"
-                   "       [--procedural seed large_n small_n weather_n] [--bruneton] [--flags march_mode_flags]\n");
+                   "       [--procedural seed large_n small_n weather_n] [--bruneton] [--flags march_mode_flags] [--budget min_step_m min_steps]\n");
             return a == "--help" ? 0 : 1;
         }
     }
@@ -67,7 +71,7 @@ int main(int argc, char** argv) {
     SYM(cs_create) SYM(cs_destroy) SYM(cs_last_error) SYM(cs_backend_name) SYM(cs_load_texture_files) SYM(cs_build_transmittance_lut)
     SYM(cs_build_sky_lut) SYM(cs_resize) SYM(cs_set_march_config) SYM(cs_render_frame_host) SYM(cs_settings_demo) SYM(cs_frame_state_init)
     SYM(cs_frame_advance) SYM(cs_fill_cloud_params) SYM(cs_generate_noise) SYM(cs_noise_params_default) SYM(cs_upload_textures)
-    SYM(cs_set_transmittance_parametrisation)
+    SYM(cs_set_transmittance_parametrisation) SYM(cs_set_step_budget)
 
     cs_context* ctx = nullptr;
     if (cs_create(device, &ctx) != CS_OK) { fprintf(stderr, "cs_create failed (backend %s)\n", cs_backend_name()); return 3; }
@@ -87,6 +91,7 @@ int main(int argc, char** argv) {
     CK(cs_build_transmittance_lut(ctx));
     CK(cs_resize(ctx, W, H));
     CK(cs_set_march_config(ctx, P, cone, mode == CS_MODE_STRICT ? mode : (mode | flags)));
+    CK(cs_set_step_budget(ctx, budget_len, budget_min));
     cs_sky_settings s; cs_settings_demo(&s);
     if (coverage >= 0) s.cloud_coverage = coverage;
     if (density >= 0) s.density = density;
