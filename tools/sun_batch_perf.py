@@ -8,7 +8,7 @@ import torch
 import cloudsky_b200 as cs
 from cloudsky_b200 import assets
 
-lib = cs.load_product()
+lib = cs.Library(sys.argv[sys.argv.index("--lib") + 1]) if "--lib" in sys.argv else cs.load_product()
 large, small, weather, _ = assets.load_default_textures()
 W, H, P, cone, N = 2048, 1024, 128, 7, 8
 th = np.pi * (np.arange(N) + 0.5) / N
