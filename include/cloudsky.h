@@ -108,7 +108,8 @@ typedef struct cs_counters {
 } cs_counters;
 
 /* march mode flags for cs_set_march_config */
-#define CS_MODE_FAST 0   /* product kernel: FMA contraction, fast intrinsics, exact-zero skips */
+#define CS_MODE_FAST 0   /* product kernel: fast intrinsics and exact-zero skips inside density(); sample positions and heights
+                          * in the shader's own fp32 roundings (the reference's rounding trajectory)                      */
 #define CS_MODE_STRICT 1 /* same operation order as the oracle, --fmad=false, IEEE div/sqrt  */
 /* Optional flag for CS_MODE_FAST (mode = CS_MODE_FAST | CS_MODE_EARLY_OUT), NOT reference behaviour (the reference runs all
  * primary steps even after T ~ 0, clouds.glsl:172): stop marching a ray once its transmittance T < 2^-12.  alpha = 1 - T
@@ -234,8 +235,8 @@ int cs_write_sky_lut(cs_context* ctx, const uint16_t* half4, size_t bytes);
 int cs_resize(cs_context* ctx, int width, int height);
 /* Step-count parametrisation (extension; the reference is fixed at 128 primary steps,
  * clouds.glsl:228, and 6 cone + 1 distant light samples, clouds.glsl:186-199).
- * mode = CS_MODE_FAST or CS_MODE_STRICT.  SURVEY §8(d) rule: cone sample j uses
- * RANDOM_VECTORS[j % 6] * j and mip j, LODs clamp to the last mip. */
+ * mode = CS_MODE_STRICT, or CS_MODE_FAST optionally OR-ed with CS_MODE_EARLY_OUT and with one of CS_MODE_TEX / CS_MODE_HALF.
+ * SURVEY §8(d) rule: cone sample j uses RANDOM_VECTORS[j % 6] * j and mip j, LODs clamp to the last mip. */
 int cs_set_march_config(cs_context* ctx, int primary_steps, int cone_samples, int mode);
 /* Enable/disable the device work counters (slower instrumented kernel when enabled). */
 /* Adaptive primary step count per direction (extension; the reference's own unimplemented hint "Take fewer steps towards
